@@ -1,0 +1,62 @@
+"""CPU oracle: the denoising-loop bodies of the reference pipelines, driven with
+pre-computed prompt / ID embeddings (the preprocessing that produces them is out of scope).
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Follows:
+  pipline_StableDiffusion_ConsistentID.py:533-579     SD1.5 loop (cat latents x2, scale_model_input,
+        prompt switch at ``i <= start_merge_step``, unet, CFG combine, scheduler.step)
+  pipline_StableDiffusionXL_ConsistentID.py:608-667   SDXL loop (+ add_text_embeds / add_time_ids switch)
+Batch extension (SURVEY.md 8a "Batch note"): the reference runs batch 1 only; batch B here means
+B independent latents sharing one identity's embeddings, i.e. exactly B batch-1 reference runs.
+"""
+from __future__ import annotations
+
+import torch
+
+
+@torch.no_grad()
+def denoise_sd15(unet, scheduler, latents, null_embeds, augmented_embeds, text_embeds, num_inference_steps,
+                 guidance_scale=5.0, start_merge_step=0, callback=None):
+    """latents [B,4,h,w] (already scaled by init_noise_sigma); *_embeds [1,81,cad]."""
+    b = latents.shape[0]
+    scheduler.set_timesteps(num_inference_steps, device=latents.device)
+    for i, t in enumerate(scheduler.timesteps):
+        x_in = torch.cat([latents] * 2)
+        x_in = scheduler.scale_model_input(x_in, t)
+        cond = text_embeds if i <= start_merge_step else augmented_embeds
+        ehs = torch.cat([null_embeds.expand(b, -1, -1), cond.expand(b, -1, -1)], dim=0)
+        eps = unet(x_in, t, encoder_hidden_states=ehs, cross_attention_kwargs={}).sample
+        eps_u, eps_c = eps.chunk(2)
+        eps = eps_u + guidance_scale * (eps_c - eps_u)
+        latents = scheduler.step(eps, t, latents).prev_sample
+        if callback is not None:
+            callback(i, t, latents)
+    return latents
+
+
+@torch.no_grad()
+def denoise_sdxl(unet, scheduler, latents, neg_text_only, pos_text_only, neg_facial, pos_facial,
+                 neg_pooled, pooled_text_only, pooled_facial, add_time_ids, num_inference_steps,
+                 guidance_scale=7.5, start_merge_step=0, callback=None):
+    """Embeds [1,81,2048]; pooled [1,1280]; add_time_ids [1,6] (same for both CFG halves)."""
+    b = latents.shape[0]
+    scheduler.set_timesteps(num_inference_steps, device=latents.device)
+    time_ids = torch.cat([add_time_ids.expand(b, -1)] * 2, dim=0)
+    for i, t in enumerate(scheduler.timesteps):
+        x_in = torch.cat([latents] * 2)
+        x_in = scheduler.scale_model_input(x_in, t)
+        if i <= start_merge_step:
+            ehs = torch.cat([neg_text_only.expand(b, -1, -1), pos_text_only.expand(b, -1, -1)], dim=0)
+            pooled = torch.cat([neg_pooled.expand(b, -1), pooled_text_only.expand(b, -1)], dim=0)
+        else:
+            ehs = torch.cat([neg_facial.expand(b, -1, -1), pos_facial.expand(b, -1, -1)], dim=0)
+            pooled = torch.cat([neg_pooled.expand(b, -1), pooled_facial.expand(b, -1)], dim=0)
+        eps = unet(x_in, t, encoder_hidden_states=ehs, cross_attention_kwargs={},
+                   added_cond_kwargs={"text_embeds": pooled, "time_ids": time_ids}).sample
+        eps_u, eps_c = eps.chunk(2)
+        eps = eps_u + guidance_scale * (eps_c - eps_u)
+        latents = scheduler.step(eps, t, latents).prev_sample
+        if callback is not None:
+            callback(i, t, latents)
+    return latents
