@@ -1,0 +1,387 @@
+// libcidb200.so - C-ABI entry points (include/cidb200.h) for the ConsistentID denoising hot path on sm_100a.
+// Host side: argument checking, TMA tensor-map encoding (driver entry point resolved at run time so the
+// library links without libcuda), kernel selection and launch on the caller's stream.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include <cudaTypedefs.h>
+
+#include "../../include/cidb200.h"
+#include "attn_tc.cuh"
+#include "elementwise.cuh"
+#include "gemm_tc.cuh"
+
+using namespace cid;
+
+namespace {
+
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+  return code;
+}
+#define CID_CHECK_LAUNCH(name)                                                                   \
+  do {                                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                                        \
+    if (e__ != cudaSuccess) return fail(CID_ERR_CUDA, "%s launch: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+std::once_flag g_encode_once;
+void resolve_encode() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess)
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+}
+
+// rank-R tiled map over 16-bit elements, 128B swizzle; dims[0] is the contiguous dimension.
+int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+             const cuuint32_t* box) {
+  std::call_once(g_encode_once, resolve_encode);
+  if (!g_encode) return fail(CID_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(CID_ERR_ARG, "TMA base %p not 16-byte aligned", base);
+  for (int i = 0; i + 1 < rank; ++i)
+    if (strides_bytes[i] % 16 != 0) return fail(CID_ERR_ARG, "TMA stride[%d]=%llu not a multiple of 16 bytes", i, (unsigned long long)strides_bytes[i]);
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CID_ERR_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", int(r), rank);
+  return 0;
+}
+int map_2d(CUtensorMap* m, const void* base, long long inner, long long rows, long long pitch_elems, int box_rows) {
+  cuuint64_t dims[2] = {cuuint64_t(inner), cuuint64_t(rows)};
+  cuuint64_t str[1] = {cuuint64_t(pitch_elems) * 2};
+  cuuint32_t box[2] = {64, cuuint32_t(box_rows)};
+  return make_map(m, base, 2, dims, str, box);
+}
+
+template <typename K>
+int set_smem(K kernel, int bytes, const char* name) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return fail(CID_ERR_CUDA, "cudaFuncSetAttribute(%s, %d B): %s", name, bytes, cudaGetErrorString(e));
+  return 0;
+}
+
+int grid_for(long long work_items, int block) {
+  long long g = (work_items + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return int(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+template <int BN, int STAGES>
+int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
+  using SM = GemmSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    int rc = set_smem(gemm_tc_kernel<BN, STAGES>, SM::TOTAL, "gemm_tc_kernel");
+    if (rc) return rc;
+    configured = true;
+  }
+  dim3 grid((g.N + BN - 1) / BN, m_tiles);
+  gemm_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, SM::TOTAL, st>>>(a1, a2, b, g);
+  CID_CHECK_LAUNCH("gemm_tc_kernel");
+  return 0;
+}
+int dispatch_gemm(int bn, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
+  switch (bn) {
+    case 160: return launch_gemm<160, 3>(a1, a2, b, g, m_tiles, st);
+    case 64: return launch_gemm<64, 4>(a1, a2, b, g, m_tiles, st);
+    case 16: return launch_gemm<16, 4>(a1, a2, b, g, m_tiles, st);
+  }
+  return fail(CID_ERR_UNSUPPORTED, "no GEMM instantiation for tile N %d", bn);
+}
+
+int d_pad_for(int d) {
+  if (d <= 0 || d % 8) return -1;
+  if (d <= 32) return 32;
+  if (d <= 48) return 48;
+  if (d <= 64) return 64;
+  if (d <= 80) return 80;
+  if (d <= 128) return 128;
+  if (d <= 160) return 160;
+  return -1;
+}
+
+template <int D_PAD>
+int launch_attn_self(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
+  using C = AttnCfg<D_PAD>;
+  static bool configured = false;
+  if (!configured) { int rc = set_smem(attn_self_kernel<D_PAD>, C::TOTAL, "attn_self_kernel"); if (rc) return rc; configured = true; }
+  dim3 grid((a.Nq + 127) / 128, a.H, a.B);
+  attn_self_kernel<D_PAD><<<grid, ATTN_THREADS, C::TOTAL, st>>>(q, k, v, a);
+  CID_CHECK_LAUNCH("attn_self_kernel");
+  return 0;
+}
+template <int D_PAD>
+int launch_attn_cross(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
+  using C = CrossCfg<D_PAD>;
+  static bool configured = false;
+  if (!configured) { int rc = set_smem(attn_cross_kernel<D_PAD>, C::TOTAL, "attn_cross_kernel"); if (rc) return rc; configured = true; }
+  dim3 grid((a.Nq + 127) / 128, a.H, a.B);
+  attn_cross_kernel<D_PAD><<<grid, 128, C::TOTAL, st>>>(q, k, v, a);
+  CID_CHECK_LAUNCH("attn_cross_kernel");
+  return 0;
+}
+
+// Q/K style map: [B, N, H, d] view, row pitch `pitch` elements, box {64, box_rows, 1, 1}
+int map_qk(CUtensorMap* m, const void* base, int B, int N, int H, int d, long long pitch, int box_rows) {
+  cuuint64_t dims[4] = {cuuint64_t(d), cuuint64_t(N), cuuint64_t(H), cuuint64_t(B)};
+  cuuint64_t str[3] = {cuuint64_t(pitch) * 2, cuuint64_t(d) * 2, cuuint64_t(N) * cuuint64_t(pitch) * 2};
+  cuuint32_t box[4] = {64, cuuint32_t(box_rows), 1, 1};
+  return make_map(m, base, 4, dims, str, box);
+}
+int map_vt(CUtensorMap* m, const void* base, int BH, int d, int Nkv, int d_pad) {
+  cuuint64_t dims[3] = {cuuint64_t(Nkv), cuuint64_t(d), cuuint64_t(BH)};
+  cuuint64_t str[2] = {cuuint64_t(Nkv) * 2, cuuint64_t(Nkv) * cuuint64_t(d) * 2};
+  cuuint32_t box[3] = {64, cuuint32_t(d_pad), 1};
+  return make_map(m, base, 3, dims, str, box);
+}
+
+}  // namespace
+
+extern "C" {
+
+int cid_version(void) { return 100; }
+const char* cid_last_error(void) { return g_err; }
+
+int cid_gemm_tile_n(int N, int epi) {
+  if (epi == CID_EPI_GEGLU) {
+    if (N % 160 == 0) return 160;
+    if (N % 64 == 0) return 64;
+    return -1;
+  }
+  if (N % 160 == 0) return 160;
+  if (N <= 16) return 16;
+  if (N % 64 == 0) return 64;
+  return 160;
+}
+
+int cid_gemm(const void* A, long long lda, const void* A2, long long lda2, int K1, int K2, const void* B, void* C,
+             long long ldc, int M, int N, const void* bias, const void* residual, long long ldr, const void* rowbias,
+             int rows_per_group, long long ld_rowbias, int epi, void* Vt, int n_split, int heads, int hdim, int ntok,
+             float out_scale, int dtype, void* stream) {
+  if (!A || !B || !C || M <= 0 || N <= 0) return fail(CID_ERR_ARG, "cid_gemm: null pointer or empty problem (M=%d N=%d)", M, N);
+  if (K1 <= 0 || K1 % 64 || K2 < 0 || K2 % 64) return fail(CID_ERR_ARG, "cid_gemm: K1=%d K2=%d must be multiples of 64", K1, K2);
+  if (K2 > 0 && !A2) return fail(CID_ERR_ARG, "cid_gemm: K2 > 0 without A2");
+  const int bn = cid_gemm_tile_n(N, epi);
+  if (bn < 0) return fail(CID_ERR_UNSUPPORTED, "cid_gemm: GEGLU needs N %% 64 == 0 (N=%d)", N);
+  if (epi == CID_EPI_QKV && (!Vt || n_split % 32 || heads <= 0 || hdim <= 0 || ntok <= 0 || M % ntok))
+    return fail(CID_ERR_ARG, "cid_gemm: bad QKV epilogue arguments");
+  CUtensorMap ta1, ta2, tb;
+  int rc;
+  if ((rc = map_2d(&ta1, A, K1, M, lda, 128))) return rc;
+  if (K2 > 0) { if ((rc = map_2d(&ta2, A2, K2, M, lda2, 128))) return rc; } else ta2 = ta1;
+  if ((rc = map_2d(&tb, B, K1 + K2, N, K1 + K2, bn))) return rc;
+  GemmArgs g{};
+  g.M = M; g.N = N; g.kblocks_a1 = K1 / 64; g.kblocks_a2 = K2 / 64; g.taps = 1; g.a_mode = A_GEMM;
+  g.C = C; g.ldc = ldc; g.bias = bias; g.residual = residual; g.ldr = ldr;
+  g.rowbias = rowbias; g.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; g.ld_rowbias = ld_rowbias;
+  g.epi = epi; g.is_bf16 = dtype == CID_BF16; g.Vt = Vt; g.n_split = n_split; g.heads = heads; g.hdim = hdim; g.ntok = ntok;
+  g.out_scale = out_scale;
+  return dispatch_gemm(bn, ta1, ta2, tb, g, (M + 127) / 128, static_cast<cudaStream_t>(stream));
+}
+
+int cid_conv3x3(const void* X, const void* Wt, void* Y, long long ldy, int NB, int H, int W, int Cin, int Cout, int stride2,
+                const void* bias, const void* residual, long long ldr, const void* rowbias, long long ld_rowbias,
+                float out_scale, int dtype, void* stream) {
+  if (!X || !Wt || !Y || NB <= 0 || H <= 0 || W <= 0) return fail(CID_ERR_ARG, "cid_conv3x3: null pointer or empty problem");
+  if (Cin % 64 || Cout <= 0) return fail(CID_ERR_ARG, "cid_conv3x3: Cin=%d must be a multiple of 64", Cin);
+  GemmArgs g{};
+  if (W >= 128) { g.TW = 128; g.TH = 1; g.TN = 1; }
+  else {
+    g.TW = W; g.TH = 128 / W; if (g.TH > H) g.TH = H;
+    g.TN = (g.TH == H) ? (128 / (W * H)) : 1;
+    if (g.TN < 1) g.TN = 1;
+    if (g.TN > NB) g.TN = NB;
+  }
+  g.tiles_x = (W + g.TW - 1) / g.TW; g.tiles_y = (H + g.TH - 1) / g.TH;
+  const int tiles_n = (NB + g.TN - 1) / g.TN;
+  const int m_tiles = g.tiles_x * g.tiles_y * tiles_n;
+  const int bn = cid_gemm_tile_n(Cout, CID_EPI_STORE);
+  CUtensorMap ta, tb;
+  int rc;
+  if (!stride2) {
+    cuuint64_t dims[4] = {cuuint64_t(Cin), cuuint64_t(W), cuuint64_t(H), cuuint64_t(NB)};
+    cuuint64_t str[3] = {cuuint64_t(Cin) * 2, cuuint64_t(W) * Cin * 2, cuuint64_t(H) * W * Cin * 2};
+    cuuint32_t box[4] = {64, cuuint32_t(g.TW), cuuint32_t(g.TH), cuuint32_t(g.TN)};
+    if ((rc = make_map(&ta, X, 4, dims, str, box))) return rc;
+  } else {
+    cuuint64_t dims[5] = {cuuint64_t(Cin), cuuint64_t(W), cuuint64_t(H), 4, cuuint64_t(NB)};
+    cuuint64_t str[4] = {cuuint64_t(Cin) * 2, cuuint64_t(W) * Cin * 2, cuuint64_t(H) * W * Cin * 2, cuuint64_t(4) * H * W * Cin * 2};
+    cuuint32_t box[5] = {64, cuuint32_t(g.TW), cuuint32_t(g.TH), 1, cuuint32_t(g.TN)};
+    if ((rc = make_map(&ta, X, 5, dims, str, box))) return rc;
+  }
+  if ((rc = map_2d(&tb, Wt, 9LL * Cin, Cout, 9LL * Cin, bn))) return rc;
+  g.M = NB * H * W; g.N = Cout; g.kblocks_a1 = Cin / 64; g.kblocks_a2 = 0; g.taps = 9;
+  g.a_mode = stride2 ? A_CONV_S2 : A_CONV; g.W = W; g.H = H; g.NB = NB;
+  g.C = Y; g.ldc = ldy; g.bias = bias; g.residual = residual; g.ldr = ldr;
+  g.rowbias = rowbias; g.rows_per_group = H * W; g.ld_rowbias = ld_rowbias;
+  g.epi = EPI_STORE; g.is_bf16 = dtype == CID_BF16; g.out_scale = out_scale;
+  return dispatch_gemm(bn, ta, ta, tb, g, m_tiles, static_cast<cudaStream_t>(stream));
+}
+
+int cid_attn_self(const void* Q, long long q_pitch, const void* K, long long k_pitch, const void* Vt, void* O, long long ldo,
+                  int B, int H, int N, int d, int dtype, void* stream) {
+  if (!Q || !K || !Vt || !O || B <= 0 || H <= 0 || N <= 0) return fail(CID_ERR_ARG, "cid_attn_self: null pointer or empty problem");
+  const int dp = d_pad_for(d);
+  if (dp < 0) return fail(CID_ERR_UNSUPPORTED, "cid_attn_self: head dim %d unsupported (multiple of 8, <= 160)", d);
+  if (N % 8) return fail(CID_ERR_UNSUPPORTED, "cid_attn_self: N=%d must be a multiple of 8", N);
+  CUtensorMap tq, tk, tv; int rc;
+  if ((rc = map_qk(&tq, Q, B, N, H, d, q_pitch, 128))) return rc;
+  if ((rc = map_qk(&tk, K, B, N, H, d, k_pitch, 128))) return rc;
+  if ((rc = map_vt(&tv, Vt, B * H, d, N, dp))) return rc;
+  AttnArgs a{}; a.B = B; a.H = H; a.Nq = N; a.Nkv = N; a.d = d; a.scale_log2 = 1.4426950408889634f / sqrtf(float(d));
+  a.O = O; a.ldo = ldo; a.is_bf16 = dtype == CID_BF16;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (dp) {
+    case 32: return launch_attn_self<32>(tq, tk, tv, a, st);
+    case 48: return launch_attn_self<48>(tq, tk, tv, a, st);
+    case 64: return launch_attn_self<64>(tq, tk, tv, a, st);
+    case 80: return launch_attn_self<80>(tq, tk, tv, a, st);
+    case 128: return launch_attn_self<128>(tq, tk, tv, a, st);
+    case 160: return launch_attn_self<160>(tq, tk, tv, a, st);
+  }
+  return fail(CID_ERR_UNSUPPORTED, "cid_attn_self: no instantiation for padded head dim %d", dp);
+}
+
+int cid_attn_cross(const void* Q, long long q_pitch, const void* Kcat, const void* Vtcat, void* O, long long ldo, int B, int H,
+                   int N, int d, int n_text, int n_ip, float ip_scale, int dtype, void* stream) {
+  if (!Q || !Kcat || !Vtcat || !O || B <= 0 || H <= 0 || N <= 0) return fail(CID_ERR_ARG, "cid_attn_cross: null pointer or empty problem");
+  if (n_text <= 0 || n_text > 80 || n_ip < 0 || n_ip > 16) return fail(CID_ERR_UNSUPPORTED, "cid_attn_cross: n_text=%d (<=80), n_ip=%d (<=16)", n_text, n_ip);
+  const int dp = d_pad_for(d);
+  if (dp < 0) return fail(CID_ERR_UNSUPPORTED, "cid_attn_cross: head dim %d unsupported", d);
+  CUtensorMap tq, tk, tv; int rc;
+  if ((rc = map_qk(&tq, Q, B, N, H, d, q_pitch, 128))) return rc;
+  if ((rc = map_qk(&tk, Kcat, B, 96, H, d, (long long)H * d, 96))) return rc;
+  if ((rc = map_vt(&tv, Vtcat, B * H, d, 96, dp))) return rc;
+  AttnArgs a{}; a.B = B; a.H = H; a.Nq = N; a.Nkv = 96; a.d = d; a.scale_log2 = 1.4426950408889634f / sqrtf(float(d));
+  a.O = O; a.ldo = ldo; a.is_bf16 = dtype == CID_BF16; a.n_text = n_text; a.ip_off = 80; a.n_ip = n_ip; a.ip_scale = ip_scale;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (dp) {
+    case 32: return launch_attn_cross<32>(tq, tk, tv, a, st);
+    case 48: return launch_attn_cross<48>(tq, tk, tv, a, st);
+    case 64: return launch_attn_cross<64>(tq, tk, tv, a, st);
+    case 80: return launch_attn_cross<80>(tq, tk, tv, a, st);
+    case 128: return launch_attn_cross<128>(tq, tk, tv, a, st);
+    case 160: return launch_attn_cross<160>(tq, tk, tv, a, st);
+  }
+  return fail(CID_ERR_UNSUPPORTED, "cid_attn_cross: no instantiation for padded head dim %d", dp);
+}
+
+int cid_pack_cross_kv(const void* k_text, const void* v_text, const void* k_ip, const void* v_ip, void* k_cat, void* vt_cat,
+                      int B, int C, int heads, int n_text, int n_ip, void* stream) {
+  if (!k_text || !v_text || !k_cat || !vt_cat || (n_ip > 0 && (!k_ip || !v_ip))) return fail(CID_ERR_ARG, "cid_pack_cross_kv: null pointer");
+  if (n_text > 80 || n_ip > 16 || C % heads) return fail(CID_ERR_ARG, "cid_pack_cross_kv: bad sizes");
+  const long long total = (long long)B * 96 * C;
+  pack_cross_kv_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      (const uint16_t*)k_text, (const uint16_t*)v_text, (const uint16_t*)k_ip, (const uint16_t*)v_ip, (uint16_t*)k_cat,
+      (uint16_t*)vt_cat, B, C, heads, n_text, n_ip, 80, 96);
+  CID_CHECK_LAUNCH("pack_cross_kv_kernel");
+  return 0;
+}
+
+int cid_gn_stats(const void* x1, int C1, const void* x2, int C2, int NB, int HW, int groups, float* sums, int dtype, void* stream) {
+  const int C = C1 + C2;
+  if (!x1 || !sums || C1 % 8 || C2 % 8 || C % groups || (C2 > 0 && !x2)) return fail(CID_ERR_ARG, "cid_gn_stats: bad arguments (C1=%d C2=%d groups=%d)", C1, C2, groups);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * NB * groups, st);
+  if (e != cudaSuccess) return fail(CID_ERR_CUDA, "cid_gn_stats memset: %s", cudaGetErrorString(e));
+  const int V = C / 8;
+  const int zchunks = (V + 255) / 256;
+  int slabs = (148 * 8) / (NB * zchunks); if (slabs < 1) slabs = 1;
+  const int tpp = 256 / (V < 256 ? V : 256);
+  const int max_slabs = (HW + tpp - 1) / tpp; if (slabs > max_slabs) slabs = max_slabs;
+  gn_stats_kernel<<<dim3(slabs, NB, zchunks), 256, 0, st>>>((const uint16_t*)x1, C1, (const uint16_t*)x2, C2, HW, groups, sums, dtype == CID_BF16);
+  CID_CHECK_LAUNCH("gn_stats_kernel");
+  return 0;
+}
+int cid_gn_apply(const void* x1, int C1, const void* x2, int C2, int NB, int HW, int groups, const float* sums, const void* gamma,
+                 const void* beta, float eps, int silu, void* y, int dtype, void* stream) {
+  const int C = C1 + C2;
+  if (!x1 || !sums || !gamma || !beta || !y || C1 % 8 || C2 % 8 || C % groups) return fail(CID_ERR_ARG, "cid_gn_apply: bad arguments");
+  const long long total = (long long)NB * HW * (C / 8);
+  gn_apply_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      (const uint16_t*)x1, C1, (const uint16_t*)x2, C2, HW, groups, sums, (const uint16_t*)gamma, (const uint16_t*)beta, eps, silu,
+      (uint16_t*)y, total, dtype == CID_BF16);
+  CID_CHECK_LAUNCH("gn_apply_kernel");
+  return 0;
+}
+int cid_layernorm(const void* x, const void* gamma, const void* beta, void* y, long long rows, int C, float eps, int dtype, void* stream) {
+  if (!x || !gamma || !beta || !y || C % 8 || C > 2048) return fail(CID_ERR_ARG, "cid_layernorm: C=%d must be a multiple of 8 and <= 2048", C);
+  const int rows_per_block = 8;
+  layernorm_kernel<<<(unsigned)((rows + rows_per_block - 1) / rows_per_block), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      (const uint16_t*)x, (const uint16_t*)gamma, (const uint16_t*)beta, (uint16_t*)y, rows, C, eps, dtype == CID_BF16);
+  CID_CHECK_LAUNCH("layernorm_kernel");
+  return 0;
+}
+int cid_upsample2x(const void* x, void* y, int NB, int H, int W, int C, void* stream) {
+  if (!x || !y || C % 8) return fail(CID_ERR_ARG, "cid_upsample2x: bad arguments");
+  const long long total = (long long)NB * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>((const uint4*)x, (uint4*)y, NB, H, W, C / 8, total);
+  CID_CHECK_LAUNCH("upsample2x_kernel");
+  return 0;
+}
+int cid_phase_split(const void* x, void* y, int NB, int H, int W, int C, void* stream) {
+  if (!x || !y || C % 8 || H % 2 || W % 2) return fail(CID_ERR_ARG, "cid_phase_split: needs even H, W and C %% 8 == 0");
+  const long long total = (long long)NB * H * W * (C / 8);
+  phase_split_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>((const uint4*)x, (uint4*)y, NB, H, W, C / 8, total);
+  CID_CHECK_LAUNCH("phase_split_kernel");
+  return 0;
+}
+int cid_nchw_to_nhwc_pad(const void* x, void* y, int NB, int Cin, int HW, int CP, const float* scale_dev, int dtype, void* stream) {
+  if (!x || !y || CP % 8 || CP < Cin) return fail(CID_ERR_ARG, "cid_nchw_to_nhwc_pad: bad arguments");
+  const long long total = (long long)NB * HW * (CP / 8);
+  nchw_to_nhwc_pad_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>((const uint16_t*)x, (uint16_t*)y, NB, Cin, HW, CP, scale_dev, dtype == CID_BF16);
+  CID_CHECK_LAUNCH("nchw_to_nhwc_pad_kernel");
+  return 0;
+}
+int cid_rows_to_nchw(const void* x, int ld, void* y, int NB, int Cout, int HW, void* stream) {
+  if (!x || !y) return fail(CID_ERR_ARG, "cid_rows_to_nchw: null pointer");
+  const long long total = (long long)NB * Cout * HW;
+  rows_to_nchw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>((const uint16_t*)x, ld, (uint16_t*)y, NB, Cout, HW);
+  CID_CHECK_LAUNCH("rows_to_nchw_kernel");
+  return 0;
+}
+int cid_add_inplace(void* y, const void* x, long long n_elems, int dtype, void* stream) {
+  if (!x || !y || n_elems % 8) return fail(CID_ERR_ARG, "cid_add_inplace: n_elems must be a multiple of 8");
+  add_inplace_kernel<<<grid_for(n_elems / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>((uint4*)y, (const uint4*)x, n_elems / 8, dtype == CID_BF16);
+  CID_CHECK_LAUNCH("add_inplace_kernel");
+  return 0;
+}
+int cid_timestep_embed(const float* t_dev, int t_stride, int rows, int dim, void* out, long long ld, int col0, int dtype, void* stream) {
+  if (!t_dev || !out || dim % 2) return fail(CID_ERR_ARG, "cid_timestep_embed: bad arguments");
+  timestep_embed_kernel<<<grid_for((long long)rows * dim / 2, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(t_dev, t_stride, rows, dim, (uint16_t*)out, ld, col0, dtype == CID_BF16);
+  CID_CHECK_LAUNCH("timestep_embed_kernel");
+  return 0;
+}
+int cid_skinny_linear(const void* x, long long ldx, const void* W, const void* bias, void* y, long long ldy, int M, int N, int K,
+                      int silu_in, int accumulate, int dtype, void* stream) {
+  if (!x || !W || !y || K % 8 || K > 4096 || M <= 0) return fail(CID_ERR_ARG, "cid_skinny_linear: K=%d must be a multiple of 8 and <= 4096", K);
+  static bool configured = false;
+  if (!configured) { int rc = set_smem(skinny_linear_kernel, 16 * 4096 * 2, "skinny_linear_kernel"); if (rc) return rc; configured = true; }
+  skinny_linear_kernel<<<(N + 7) / 8, 256, 16 * K * 2, static_cast<cudaStream_t>(stream)>>>(
+      (const uint16_t*)x, ldx, (const uint16_t*)W, (const uint16_t*)bias, (uint16_t*)y, ldy, M, N, K, silu_in, accumulate, dtype == CID_BF16);
+  CID_CHECK_LAUNCH("skinny_linear_kernel");
+  return 0;
+}
+int cid_cfg_sched_step(const void* eps, int ld_eps, float* x, float* x0_prev, void* x16, void* next_in, int CP, int B, int HW,
+                       float guidance, const float* coef_table, const int* step_dev, int dtype, void* stream) {
+  if (!eps || !x || !x0_prev || !x16 || !coef_table || !step_dev || ld_eps % 4 || (next_in && CP % 8)) return fail(CID_ERR_ARG, "cid_cfg_sched_step: bad arguments");
+  cfg_sched_step_kernel<<<grid_for((long long)B * HW, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      (const uint16_t*)eps, ld_eps, x, x0_prev, (uint16_t*)x16, (uint16_t*)next_in, CP, B, HW, guidance, coef_table, step_dev, dtype == CID_BF16);
+  CID_CHECK_LAUNCH("cfg_sched_step_kernel");
+  return 0;
+}
+int cid_latents_to_input(const float* x, void* next_in, int CP, int B, int HW, const float* coef_table, int dtype, void* stream) {
+  if (!x || !next_in || !coef_table || CP % 8) return fail(CID_ERR_ARG, "cid_latents_to_input: bad arguments");
+  latents_to_input_kernel<<<grid_for((long long)B * HW, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, (uint16_t*)next_in, CP, B, HW, coef_table, dtype == CID_BF16);
+  CID_CHECK_LAUNCH("latents_to_input_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,452 @@
+// tcgen05 attention kernels for the ConsistentID processors (sm_100a).
+//
+//  attn_self_kernel   Consistent_AttProcessor core (attention.py:152-159): softmax(scale * Q K^T) V per (sample, head),
+//                     flash-style over 128-key tiles, never materialising the [2B*H, N, N] matrix the reference writes.
+//  attn_cross_kernel  Consistent_IPAttProcessor core (attention.py:259-279): ONE Q K_cat^T MMA over
+//                     K_cat = [77 text keys | pad | 4 id keys | pad] (96 rows), TWO independent softmaxes
+//                     (text range / id range), two P V MMAs into separate accumulators, mixed in the epilogue as
+//                     O_text / l_text + scale * O_ip / l_ip.
+//
+// Layouts (all 16-bit, K-major for UMMA):
+//   Q, K   [B, N, H, d] views of the projection outputs (row pitch = projection width) - 4-D TMA maps {d, N, H, B},
+//          box {64, 128|96}: head dims 40/80/160 are zero-filled by TMA up to the 64-element swizzle row.
+//   V^T    [B*H, d, Nkv] (keys contiguous; written transposed by the QKV GEMM epilogue) - 3-D map {Nkv, d, B*H}.
+//   P      written by the softmax warps into 128B-swizzled smem (A operand of the second MMA).
+// TMEM: S [128 x 128 fp32] at column 0, P*V partial at column 128 (self) / O_text, O_ip (cross).
+#pragma once
+#include "common.cuh"
+
+namespace cid {
+
+struct AttnArgs {
+  int B, H, Nq, Nkv, d;
+  float scale_log2;      // d^-0.5 * log2(e)
+  void* O;               // [B, Nq, H*d], row pitch ldo elements
+  long long ldo;
+  int is_bf16;
+  int n_text, ip_off, n_ip;   // cross: key ranges [0, n_text) and [ip_off, ip_off + n_ip)
+  float ip_scale;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// write 8 consecutive 16-bit values (one 16-byte chunk) of row r, element column col (multiple of 8, < 64) of a
+// [rows x 64] K-major tile stored with the 128-byte swizzle (chunk index XOR (row & 7))
+__device__ __forceinline__ void st_sw128(uint8_t* tile, int r, int col, uint4 v) {
+  const int chunk = (col >> 3) ^ (r & 7);
+  *reinterpret_cast<uint4*>(tile + r * 128 + chunk * 16) = v;
+}
+
+constexpr int ATTN_THREADS = 192;
+
+template <int D_PAD>
+struct AttnCfg {
+  static constexpr int NCH = (D_PAD + 63) / 64;                 // 64-wide head-dim chunks
+  static constexpr int STAGES = (D_PAD <= 80) ? 2 : 1;
+  static constexpr int Q_BYTES = NCH * 16384;
+  static constexpr int K_BYTES = NCH * 16384;                   // per stage
+  static constexpr int V_CHUNK = D_PAD * 128;                   // one 64-key chunk of V^T
+  static constexpr int V_BYTES = 2 * V_CHUNK;                   // per stage
+  static constexpr int P_BYTES = 2 * 16384;
+  static constexpr int OFF_K = Q_BYTES;
+  static constexpr int OFF_V = OFF_K + STAGES * K_BYTES;
+  static constexpr int OFF_P = OFF_V + STAGES * V_BYTES;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int TOTAL = OFF_BAR + 256;
+  static constexpr int TMEM_COLS = (128 + D_PAD <= 256) ? 256 : 512;
+  static constexpr int MIN_CTAS = (TOTAL <= 115000 && TMEM_COLS == 256) ? 2 : 1;
+};
+
+template <int D_PAD>
+__global__ void __launch_bounds__(ATTN_THREADS, AttnCfg<D_PAD>::MIN_CTAS)
+attn_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmVt, const AttnArgs a) {
+  using C = AttnCfg<D_PAD>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if ((sbase & 1023u) != 0) { if (threadIdx.x == 0) printf("cid: attn smem base not 1024-aligned\n"); __trap(); }
+  const uint32_t bar0 = sbase + C::OFF_BAR;
+  // barrier map
+  const uint32_t q_full = bar0;
+  auto k_full = [&](int s) { return bar0 + 8u * (1 + s); };
+  auto k_empty = [&](int s) { return bar0 + 8u * (1 + STAGES + s); };
+  auto v_full = [&](int s) { return bar0 + 8u * (1 + 2 * STAGES + s); };
+  auto v_empty = [&](int s) { return bar0 + 8u * (1 + 3 * STAGES + s); };
+  const uint32_t s_full = bar0 + 8u * (1 + 4 * STAGES);
+  const uint32_t s_free = s_full + 8u;
+  const uint32_t p_full = s_full + 16u;
+  const uint32_t pv_full = s_full + 24u;
+  const uint32_t pv_free = s_full + 32u;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + C::OFF_BAR + 8 * (6 + 4 * STAGES));
+
+  const int warp = warp_id(), lane = lane_id();
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int T = (a.Nkv + 127) / 128;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmVt); }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int s = 0; s < STAGES; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
+      mbar_init(s_full, 1); mbar_init(s_free, 128); mbar_init(p_full, 128); mbar_init(pv_full, 1); mbar_init(pv_free, 128);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<C::TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_S = tmem, tmem_PV = tmem + 128;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, C::Q_BYTES);
+      for (int ch = 0; ch < C::NCH; ++ch) tma_load_4d(sbase + ch * 16384, &tmQ, q_full, ch * 64, q0, h, b);
+      int stage = 0; uint32_t phase = 0;
+      for (int j = 0; j < T; ++j) {
+        const int k0 = j * 128;
+        mbar_wait(k_empty(stage), phase ^ 1u);
+        mbar_expect_tx(k_full(stage), C::K_BYTES);
+        for (int ch = 0; ch < C::NCH; ++ch)
+          tma_load_4d(sbase + C::OFF_K + stage * C::K_BYTES + ch * 16384, &tmK, k_full(stage), ch * 64, k0, h, b);
+        mbar_wait(v_empty(stage), phase ^ 1u);
+        mbar_expect_tx(v_full(stage), C::V_BYTES);
+        for (int kc = 0; kc < 2; ++kc)
+          tma_load_3d(sbase + C::OFF_V + stage * C::V_BYTES + kc * C::V_CHUNK, &tmVt, v_full(stage), k0 + kc * 64, 0, b * a.H + h);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    const uint32_t idesc_s = make_idesc(128, 128, a.is_bf16);
+    const uint32_t idesc_pv = make_idesc(128, D_PAD, a.is_bf16);
+    auto issue_S = [&](int stage) {
+      const uint32_t sk = sbase + C::OFF_K + stage * C::K_BYTES;
+#pragma unroll
+      for (int ch = 0; ch < C::NCH; ++ch) {
+        const int ksteps = (D_PAD - ch * 64 >= 64) ? 4 : (D_PAD - ch * 64) / 16;
+#pragma unroll
+        for (int kk = 0; kk < ksteps; ++kk)
+          umma_ss(tmem_S, make_desc_sw128(sbase + ch * 16384 + kk * 32), make_desc_sw128(sk + ch * 16384 + kk * 32),
+                  idesc_s, (ch | kk) ? 1u : 0u);
+      }
+    };
+    mbar_wait(q_full, 0);
+    int stage = 0; uint32_t phase = 0;       // stage/phase of tile j
+    int nstage = 0; uint32_t nphase = 0;     // stage/phase of tile j+1
+    // S_0
+    mbar_wait(k_full(0), 0);
+    tc_fence_after();
+    if (lane == 0) { issue_S(0); umma_commit(s_full); umma_commit(k_empty(0)); }
+    __syncwarp();
+    if (++nstage == STAGES) { nstage = 0; nphase ^= 1u; }
+    for (int j = 0; j < T; ++j) {
+      if (j + 1 < T) {
+        mbar_wait(k_full(nstage), nphase);
+        mbar_wait(s_free, uint32_t(j & 1));            // softmax has finished reading S_j
+        tc_fence_after();
+        if (lane == 0) { issue_S(nstage); umma_commit(s_full); umma_commit(k_empty(nstage)); }
+        __syncwarp();
+        if (++nstage == STAGES) { nstage = 0; nphase ^= 1u; }
+      }
+      mbar_wait(p_full, uint32_t(j & 1));              // P_j is in smem
+      mbar_wait(v_full(stage), phase);
+      if (j > 0) mbar_wait(pv_free, uint32_t((j - 1) & 1));   // PV_{j-1} has been read out of TMEM
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sv = sbase + C::OFF_V + stage * C::V_BYTES;
+        const uint32_t sp = sbase + C::OFF_P;
+#pragma unroll
+        for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_ss(tmem_PV, make_desc_sw128(sp + kc * 16384 + kk * 32), make_desc_sw128(sv + kc * C::V_CHUNK + kk * 32),
+                    idesc_pv, (kc | kk) ? 1u : 0u);
+        umma_commit(pv_full);
+        umma_commit(v_empty(stage));
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    }
+  } else {
+    // ============================================================ softmax + output (warps 2..5, one query row per thread)
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = uint32_t(quarter * 32) << 16;
+    const int bf = a.is_bf16;
+    uint8_t* sP = smem_raw + C::OFF_P;
+    float o[D_PAD];
+#pragma unroll
+    for (int i = 0; i < D_PAD; ++i) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f, alpha_pending = 0.f;
+    const float c = a.scale_log2;
+
+    auto accumulate_pv = [&](float alpha) {
+#pragma unroll
+      for (int cc = 0; cc < D_PAD; cc += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tmem_PV + lane_off + cc, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[cc + i] = o[cc + i] * alpha + __uint_as_float(v[i]);
+      }
+    };
+
+    for (int j = 0; j < T; ++j) {
+      const int kvalid = a.Nkv - j * 128;                     // keys of this tile that exist
+      mbar_wait(s_full, uint32_t(j & 1));
+      tc_fence_after();
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int cc = 0; cc < 128; cc += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_S + lane_off + cc, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (cc + i < kvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = fast_exp2((m - m_new) * c);
+      const float mc = m_new * c;
+      // fold in the previous tile's P*V (it finished long ago; also guarantees P smem is free again)
+      if (j > 0) {
+        mbar_wait(pv_full, uint32_t((j - 1) & 1));
+        tc_fence_after();
+        accumulate_pv(alpha_pending);
+        tc_fence_before();
+        mbar_arrive(pv_free);
+      }
+      alpha_pending = alpha;
+      // pass 2: probabilities -> swizzled smem (A operand of P*V)
+      float sum = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < 128; cc += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_S + lane_off + cc, v);
+        tmem_ld_wait();
+        if (cc == 96) { tc_fence_before(); mbar_arrive(s_free); }   // S_j fully read
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = (cc + i < kvalid) ? fast_exp2(__uint_as_float(v[i]) * c - mc) : 0.f;
+          float p1 = (cc + i + 1 < kvalid) ? fast_exp2(__uint_as_float(v[i + 1]) * c - mc) : 0.f;
+          sum += p0 + p1;
+          pk[i >> 1] = pack16(p0, p1, bf);
+        }
+        uint8_t* tile = sP + (cc >> 6) * 16384;
+        const int col = cc & 63;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          st_sw128(tile, r, col + q * 8, make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]));
+      }
+      l = l * alpha + sum;
+      m = m_new;
+      fence_proxy_async();
+      mbar_arrive(p_full);
+    }
+    // last tile's P*V
+    mbar_wait(pv_full, uint32_t((T - 1) & 1));
+    tc_fence_after();
+    accumulate_pv(alpha_pending);
+    tc_fence_before();
+    const float inv = 1.f / l;
+    if (q0 + r < a.Nq) {
+      uint16_t* dst = reinterpret_cast<uint16_t*>(a.O) + ((long long)b * a.Nq + q0 + r) * a.ldo + h * a.d;
+#pragma unroll
+      for (int i = 0; i < D_PAD; i += 8) {
+        if (i < a.d) {
+          uint4 u;
+          u.x = pack16(o[i] * inv, o[i + 1] * inv, bf); u.y = pack16(o[i + 2] * inv, o[i + 3] * inv, bf);
+          u.z = pack16(o[i + 4] * inv, o[i + 5] * inv, bf); u.w = pack16(o[i + 6] * inv, o[i + 7] * inv, bf);
+          *reinterpret_cast<uint4*>(dst + i) = u;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<C::TMEM_COLS>(tmem); }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Decoupled text + id cross-attention, one 96-row key/value tile.
+template <int D_PAD>
+struct CrossCfg {
+  static constexpr int NCH = (D_PAD + 63) / 64;
+  static constexpr int KROWS = 96;
+  static constexpr int Q_BYTES = NCH * 16384;
+  static constexpr int K_CHUNK = KROWS * 128;
+  static constexpr int K_BYTES = NCH * K_CHUNK;
+  static constexpr int V_CHUNK = D_PAD * 128;
+  static constexpr int V_BYTES = 2 * V_CHUNK;
+  static constexpr int OFF_K = Q_BYTES;
+  static constexpr int OFF_V = OFF_K + K_BYTES;
+  static constexpr int OFF_P = OFF_V + V_BYTES;
+  static constexpr int OFF_BAR = OFF_P + 2 * 16384;
+  static constexpr int TOTAL = OFF_BAR + 64;
+  static constexpr int TMEM_COLS = (128 + 2 * D_PAD <= 256) ? 256 : 512;
+  static constexpr int MIN_CTAS = (TMEM_COLS == 256) ? 2 : 1;
+};
+
+template <int D_PAD>
+__global__ void __launch_bounds__(128, CrossCfg<D_PAD>::MIN_CTAS)
+attn_cross_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmVt, const AttnArgs a) {
+  using C = CrossCfg<D_PAD>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if ((sbase & 1023u) != 0) { if (threadIdx.x == 0) printf("cid: cross-attn smem base not 1024-aligned\n"); __trap(); }
+  const uint32_t bar_ld = sbase + C::OFF_BAR, bar_s = bar_ld + 8, bar_o = bar_ld + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + C::OFF_BAR + 32);
+  const int warp = warp_id(), lane = lane_id();
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_init(bar_ld, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<C::TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_S = tmem, tmem_Ot = tmem + 128, tmem_Oi = tmem + 128 + D_PAD;
+
+  if (warp == 0 && lane == 0) {
+    mbar_expect_tx(bar_ld, C::Q_BYTES + C::K_BYTES + C::V_BYTES);
+    for (int ch = 0; ch < C::NCH; ++ch) {
+      tma_load_4d(sbase + ch * 16384, &tmQ, bar_ld, ch * 64, q0, h, b);
+      tma_load_4d(sbase + C::OFF_K + ch * C::K_CHUNK, &tmK, bar_ld, ch * 64, 0, h, b);
+    }
+    for (int kc = 0; kc < 2; ++kc) tma_load_3d(sbase + C::OFF_V + kc * C::V_CHUNK, &tmVt, bar_ld, kc * 64, 0, b * a.H + h);
+    mbar_wait(bar_ld, 0);
+    tc_fence_after();
+    const uint32_t idesc_s = make_idesc(128, C::KROWS, a.is_bf16);
+#pragma unroll
+    for (int ch = 0; ch < C::NCH; ++ch) {
+      const int ksteps = (D_PAD - ch * 64 >= 64) ? 4 : (D_PAD - ch * 64) / 16;
+#pragma unroll
+      for (int kk = 0; kk < ksteps; ++kk)
+        umma_ss(tmem_S, make_desc_sw128(sbase + ch * 16384 + kk * 32),
+                make_desc_sw128(sbase + C::OFF_K + ch * C::K_CHUNK + kk * 32), idesc_s, (ch | kk) ? 1u : 0u);
+    }
+    umma_commit(bar_s);
+  }
+  __syncwarp();
+
+  const int r = warp * 32 + lane;
+  const uint32_t lane_off = uint32_t(warp * 32) << 16;
+  const int bf = a.is_bf16;
+  const float c = a.scale_log2;
+  const int t_end = a.n_text, i_beg = a.ip_off, i_end = a.ip_off + a.n_ip;
+  mbar_wait(bar_s, 0);
+  tc_fence_after();
+  float mt = -INFINITY, mi = -INFINITY;
+#pragma unroll 1
+  for (int cc = 0; cc < C::KROWS; cc += 32) {
+    uint32_t v[32];
+    tmem_ld_x32(tmem_S + lane_off + cc, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int key = cc + i; const float s = __uint_as_float(v[i]);
+      if (key < t_end) mt = fmaxf(mt, s);
+      if (key >= i_beg && key < i_end) mi = fmaxf(mi, s);
+    }
+  }
+  float lt = 0.f, li = 0.f;
+  uint8_t* sP = smem_raw + C::OFF_P;
+#pragma unroll 1
+  for (int cc = 0; cc < C::KROWS; cc += 32) {
+    uint32_t v[32];
+    tmem_ld_x32(tmem_S + lane_off + cc, v);
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      float p[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int key = cc + i + e; const float s = __uint_as_float(v[i + e]);
+        float pe = 0.f;
+        if (key < t_end) { pe = fast_exp2((s - mt) * c); lt += pe; }
+        else if (key >= i_beg && key < i_end) { pe = fast_exp2((s - mi) * c); li += pe; }
+        p[e] = pe;
+      }
+      pk[i >> 1] = pack16(p[0], p[1], bf);
+    }
+    uint8_t* tile = sP + (cc >> 6) * 16384;
+    const int col = cc & 63;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      st_sw128(tile, r, col + q * 8, make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]));
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0 && lane == 0) {
+    tc_fence_after();
+    const uint32_t idesc_pv = make_idesc(128, D_PAD, a.is_bf16);
+    const uint32_t sp = sbase + C::OFF_P, sv = sbase + C::OFF_V;
+    // text range: keys [0, 80) = 5 k-steps (rows 77..79 of K_cat / V_cat are zero padding, P is 0 there)
+#pragma unroll
+    for (int ks = 0; ks < 5; ++ks) {
+      const int kc = ks >> 2, kk = ks & 3;
+      umma_ss(tmem_Ot, make_desc_sw128(sp + kc * 16384 + kk * 32), make_desc_sw128(sv + kc * C::V_CHUNK + kk * 32), idesc_pv, ks ? 1u : 0u);
+    }
+    // id range: keys [80, 96) = k-step 5 (chunk 1, second 16-key slice)
+    umma_ss(tmem_Oi, make_desc_sw128(sp + 16384 + 32), make_desc_sw128(sv + C::V_CHUNK + 32), idesc_pv, 0u);
+    umma_commit(bar_o);
+  }
+  __syncwarp();
+  mbar_wait(bar_o, 0);
+  tc_fence_after();
+  const float wt = 1.f / lt;
+  const float wi = (a.n_ip > 0) ? a.ip_scale / li : 0.f;
+  const bool row_ok = q0 + r < a.Nq;
+  uint16_t* dst = reinterpret_cast<uint16_t*>(a.O) + ((long long)b * a.Nq + q0 + r) * a.ldo + h * a.d;
+#pragma unroll 1
+  for (int cc = 0; cc < D_PAD; cc += 16) {
+    uint32_t vt[16], vi[16];
+    tmem_ld_x16(tmem_Ot + lane_off + cc, vt);
+    tmem_ld_x16(tmem_Oi + lane_off + cc, vi);
+    tmem_ld_wait();
+    if (row_ok && cc < a.d) {
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        // reference rounds each branch to 16-bit before the mix (attention.py:264,276-279)
+        float2 tt = unpack16(pack16(__uint_as_float(vt[i]) * wt, 0.f, bf), bf);
+        float2 ii = unpack16(pack16(__uint_as_float(vi[i]) * (1.f / li), 0.f, bf), bf);
+        f[i] = tt.x + ((a.n_ip > 0) ? a.ip_scale * ii.x : 0.f);
+      }
+      (void)wi;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (cc + q * 8 < a.d) {
+          uint4 u;
+          u.x = pack16(f[q * 8 + 0], f[q * 8 + 1], bf); u.y = pack16(f[q * 8 + 2], f[q * 8 + 3], bf);
+          u.z = pack16(f[q * 8 + 4], f[q * 8 + 5], bf); u.w = pack16(f[q * 8 + 6], f[q * 8 + 7], bf);
+          *reinterpret_cast<uint4*>(dst + cc + q * 8) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<C::TMEM_COLS>(tmem); }
+}
+
+}  // namespace cid

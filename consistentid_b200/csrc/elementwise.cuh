@@ -1,0 +1,371 @@
+// HBM-bound kernels of the ConsistentID UNet hot path (sm_100a): GroupNorm statistics / apply(+SiLU, + virtual
+// channel concat), LayerNorm, nearest-2x upsample, stride-2 phase split, layout converters, sinusoidal timestep
+// embedding, skinny (M <= 64 rows) linears for the time-embedding MLPs, cross-attention K/V packing and the fused
+// CFG-combine + scheduler step.  All activations are NHWC / [tokens, C] row-major, 16-bit; 128-bit vector accesses.
+#pragma once
+#include "common.cuh"
+
+namespace cid {
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8], int bf) {
+  float2 a = unpack16(u.x, bf), b = unpack16(u.y, bf), c = unpack16(u.z, bf), d = unpack16(u.w, bf);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8], int bf) {
+  return make_uint4(pack16(f[0], f[1], bf), pack16(f[2], f[3], bf), pack16(f[4], f[5], bf), pack16(f[6], f[7], bf));
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm
+// Statistics over x = cat([x1 (C1 ch), x2 (C2 ch)], channel) in NHWC; sums[n, g, {sum, sumsq}] (fp32, pre-zeroed).
+// grid (slabs, NB); each block streams a slab of pixels with 16-byte loads, keeps per-channel partial sums in
+// registers, reduces them through smem to per-group sums and issues 2 atomics per group.
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const uint16_t* __restrict__ x1, int C1, const uint16_t* __restrict__ x2, int C2, int HW, int groups,
+                float* __restrict__ sums, int bf) {
+  __shared__ float sh[2 * 2048];                 // per-channel partial sums of this block's channel chunk
+  const int C = C1 + C2, V = C / 8;              // 8-channel vectors per pixel
+  const int n = blockIdx.y;
+  const int vbeg = blockIdx.z * 256;             // this block covers vectors [vbeg, vbeg + Vb) (<= 2048 channels)
+  const int Vb = min(V - vbeg, 256);
+  const int cbeg = vbeg * 8, Cb = Vb * 8;
+  const int tpp = blockDim.x / Vb;               // pixels processed in parallel
+  const int vec = vbeg + threadIdx.x % Vb, prow = threadIdx.x / Vb;
+  for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  if (prow < tpp) {
+    const int c0 = vec * 8;
+    const bool first = c0 < C1;
+    const uint16_t* src = first ? x1 + (size_t)n * HW * C1 + c0 : x2 + (size_t)n * HW * C2 + (c0 - C1);
+    const int pitch = first ? C1 : C2;
+    for (int p = blockIdx.x * tpp + prow; p < HW; p += gridDim.x * tpp) {
+      uint4 u = *reinterpret_cast<const uint4*>(src + (size_t)p * pitch);
+      float f[8]; unpack8(u, f, bf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { atomicAdd(&sh[c0 - cbeg + i], s[i]); atomicAdd(&sh[2048 + c0 - cbeg + i], q[i]); }
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    const int lo = max(g * cpg, cbeg), hi = min((g + 1) * cpg, cbeg + Cb);
+    if (lo >= hi) continue;
+    float a = 0.f, b = 0.f;
+    for (int c = lo; c < hi; ++c) { a += sh[c - cbeg]; b += sh[2048 + c - cbeg]; }
+    atomicAdd(&sums[((size_t)n * groups + g) * 2], a);
+    atomicAdd(&sums[((size_t)n * groups + g) * 2 + 1], b);
+  }
+}
+
+// y = [silu]((x - mean) * rstd * gamma + beta), x = cat([x1, x2]) NHWC -> y NHWC with C = C1 + C2 channels
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const uint16_t* __restrict__ x1, int C1, const uint16_t* __restrict__ x2, int C2, int HW, int groups,
+                const float* __restrict__ sums, const uint16_t* __restrict__ gamma, const uint16_t* __restrict__ beta,
+                float eps, int do_silu, uint16_t* __restrict__ y, long long total_vec, int bf) {
+  const int C = C1 + C2, V = C / 8, cpg = C / groups;
+  const float inv_n = 1.f / (float(HW) * float(cpg));
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const int vec = int(i % V);
+    const long long pix = i / V;                 // n * HW + p
+    const int n = int(pix / HW);
+    const int c0 = vec * 8;
+    const uint4 u = (c0 < C1) ? *reinterpret_cast<const uint4*>(x1 + pix * C1 + c0)
+                              : *reinterpret_cast<const uint4*>(x2 + pix * C2 + (c0 - C1));
+    float f[8]; unpack8(u, f, bf);
+    float ga[8], be[8];
+    unpack8(*reinterpret_cast<const uint4*>(gamma + c0), ga, bf);
+    unpack8(*reinterpret_cast<const uint4*>(beta + c0), be, bf);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int g = (c0 + k) / cpg;
+      const float sm = sums[((size_t)n * groups + g) * 2], sq = sums[((size_t)n * groups + g) * 2 + 1];
+      const float mean = sm * inv_n;
+      const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
+      float v = (f[k] - mean) * rsqrtf(var + eps) * ga[k] + be[k];
+      f[k] = do_silu ? silu_f(v) : v;
+    }
+    *reinterpret_cast<uint4*>(y + pix * C + c0) = pack8(f, bf);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// one warp per row, C <= 2048, C % 8 == 0
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ gamma, const uint16_t* __restrict__ beta,
+                 uint16_t* __restrict__ y, long long rows, int C, float eps, int bf) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const int V = C / 8;
+  constexpr int MAXV = 8;                        // 8 vectors * 32 lanes * 8 = 2048 channels
+  float f[MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int v = lane + j * 32;
+    if (v < V) {
+      unpack8(*reinterpret_cast<const uint4*>(x + row * C + v * 8), f[j], bf);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += f[j][k];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int v = lane + j * 32;
+    if (v < V) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float d = f[j][k] - mean; q += d * d; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int v = lane + j * 32;
+    if (v < V) {
+      float ga[8], be[8], o8[8];
+      unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), ga, bf);
+      unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), be, bf);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o8[k] = (f[j][k] - mean) * rstd * ga[k] + be[k];
+      *reinterpret_cast<uint4*>(y + row * C + v * 8) = pack8(o8, bf);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ resampling / layout
+// nearest 2x: x [NB, H, W, C] -> y [NB, 2H, 2W, C]
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int NB, int H, int W, int V, long long total_out_vec) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_out_vec; i += (long long)gridDim.x * blockDim.x) {
+    const int v = int(i % V);
+    long long p = i / V;
+    const int ox = int(p % (2 * W)); p /= (2 * W);
+    const int oy = int(p % (2 * H));
+    const int n = int(p / (2 * H));
+    y[i] = x[(((long long)n * H + (oy >> 1)) * W + (ox >> 1)) * V + v];
+  }
+}
+// stride-2 phase split: x [NB, H, W, C] -> y [NB, 4 (py*2+px), H/2, W/2, C]; y[n,ph,y',x'] = x[n, 2y'+py, 2x'+px]
+__global__ void __launch_bounds__(256)
+phase_split_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int NB, int H, int W, int V, long long total_vec) {
+  const int H2 = H / 2, W2 = W / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const int v = int(i % V);
+    long long p = i / V;
+    const int xx = int(p % W2); p /= W2;
+    const int yy = int(p % H2); p /= H2;
+    const int ph = int(p % 4);
+    const int n = int(p / 4);
+    y[i] = x[(((long long)n * H + (2 * yy + (ph >> 1))) * W + (2 * xx + (ph & 1))) * V + v];
+  }
+}
+// NCHW [NB, Cin, H, W] (16-bit) -> NHWC with CP (>= Cin, multiple of 8) channels, zero padded, times `scale`
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_pad_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int NB, int Cin, int HW, int CP,
+                        const float* __restrict__ scale_ptr, int bf) {
+  const float sc = scale_ptr ? *scale_ptr : 1.f;
+  const long long total = (long long)NB * HW * (CP / 8);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = int(i % (CP / 8));
+    const long long pix = i / (CP / 8);
+    const int n = int(pix / HW), p = int(pix % HW);
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = v * 8 + k;
+      f[k] = (c < Cin) ? load16(x, ((size_t)n * Cin + c) * HW + p, bf) * sc : 0.f;
+    }
+    *reinterpret_cast<uint4*>(y + pix * CP + v * 8) = pack8(f, bf);
+  }
+}
+// [NB*HW, ld] rows (first Cout columns valid) -> NCHW [NB, Cout, H, W]
+__global__ void __launch_bounds__(256)
+rows_to_nchw_kernel(const uint16_t* __restrict__ x, int ld, uint16_t* __restrict__ y, int NB, int Cout, int HW) {
+  const long long total = (long long)NB * Cout * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = int(i % HW);
+    const int c = int((i / HW) % Cout);
+    const int n = int(i / ((long long)HW * Cout));
+    y[i] = x[((size_t)n * HW + p) * ld + c];
+  }
+}
+// y += x (16-bit, vectorised); used for ControlNet residual injection
+__global__ void __launch_bounds__(256)
+add_inplace_kernel(uint4* __restrict__ y, const uint4* __restrict__ x, long long total_vec, int bf) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    float a[8], b[8]; unpack8(y[i], a, bf); unpack8(x[i], b, bf);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += b[k];
+    y[i] = pack8(a, bf);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ embeddings
+// diffusers get_timestep_embedding(flip_sin_to_cos=True, downscale_freq_shift=0): out[r] = [cos(t*f), sin(t*f)], f_i = 1e4^(-i/half)
+// t values: t_ptr[r * t_stride] (t_stride 0 -> one scalar broadcast to all rows).  Output rounded to 16-bit at
+// out[r*ld + col0 ..], like `t_emb.to(sample.dtype)`.
+__global__ void __launch_bounds__(128)
+timestep_embed_kernel(const float* __restrict__ t_ptr, int t_stride, int rows, int dim, uint16_t* __restrict__ out,
+                      long long ld, int col0, int bf) {
+  const int half = dim / 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * half; i += gridDim.x * blockDim.x) {
+    const int r = i / half, k = i % half;
+    const float t = t_ptr[(size_t)r * t_stride];
+    const float freq = expf(-9.210340371976184f * float(k) / float(half));   // ln(10000)
+    const float e = t * freq;
+    store16(out, (size_t)r * ld + col0 + k, cosf(e), bf);
+    store16(out, (size_t)r * ld + col0 + half + k, sinf(e), bf);
+  }
+}
+
+// y[M, N] (+)= act_in(x)[M, K] . W[N, K]^T + b     for tiny M (time-embedding MLPs, per-resnet temb projections)
+// one warp per output column; x staged in smem in 16-row slabs; W rows streamed with 16-byte loads.
+__global__ void __launch_bounds__(256)
+skinny_linear_kernel(const uint16_t* __restrict__ x, long long ldx, const uint16_t* __restrict__ w, const uint16_t* __restrict__ bias,
+                     uint16_t* __restrict__ y, long long ldy, int M, int N, int K, int silu_in, int accumulate, int bf) {
+  extern __shared__ uint16_t xs[];               // [16][K]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * (blockDim.x >> 5) + warp;
+  for (int m0 = 0; m0 < M; m0 += 16) {
+    const int mrows = min(16, M - m0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < mrows * K; i += blockDim.x) {
+      const int r = i / K, k = i % K;
+      float v = load16(x, (size_t)(m0 + r) * ldx + k, bf);
+      if (silu_in) v = silu_f(v);
+      store16(xs, (size_t)r * K + k, v, bf);
+    }
+    __syncthreads();
+    if (col < N) {
+      float acc[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) acc[r] = 0.f;
+      for (int k = lane * 8; k < K; k += 256) {
+        float wf[8]; unpack8(*reinterpret_cast<const uint4*>(w + (size_t)col * K + k), wf, bf);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          if (r < mrows) {
+            float xf[8]; unpack8(*reinterpret_cast<const uint4*>(xs + (size_t)r * K + k), xf, bf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[r] += wf[e] * xf[e];
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+      }
+      if (lane == 0) {
+        const float bv = bias ? load16(bias, col, bf) : 0.f;
+        for (int r = 0; r < mrows; ++r) {
+          float v = acc[r] + bv;
+          const size_t o = (size_t)(m0 + r) * ldy + col;
+          if (accumulate) v += load16(y, o, bf);
+          store16(y, o, v, bf);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ cross-attn K/V packing
+// K_cat[b, 96, C]: rows [0,77) = text keys, [80,84) = id keys, rest 0.   Vt_cat[b*H + h, d, 96]: same columns, transposed.
+__global__ void __launch_bounds__(256)
+pack_cross_kv_kernel(const uint16_t* __restrict__ k_text, const uint16_t* __restrict__ v_text, const uint16_t* __restrict__ k_ip,
+                     const uint16_t* __restrict__ v_ip, uint16_t* __restrict__ k_cat, uint16_t* __restrict__ vt_cat,
+                     int B, int C, int heads, int n_text, int n_ip, int ip_off, int krows) {
+  const long long total = (long long)B * krows * C;
+  const int d = C / heads;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % C);
+    const int row = int((i / C) % krows);
+    const int b = int(i / ((long long)C * krows));
+    uint16_t kv = 0, vv = 0;
+    if (row < n_text) { kv = k_text[((size_t)b * n_text + row) * C + c]; vv = v_text[((size_t)b * n_text + row) * C + c]; }
+    else if (row >= ip_off && row < ip_off + n_ip) {
+      kv = k_ip[((size_t)b * n_ip + (row - ip_off)) * C + c]; vv = v_ip[((size_t)b * n_ip + (row - ip_off)) * C + c];
+    }
+    k_cat[i] = kv;
+    const int h = c / d, dd = c % d;
+    vt_cat[(((size_t)b * heads + h) * d + dd) * krows + row] = vv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ CFG + scheduler step
+// One fused pass per denoising step (pipline_StableDiffusion_ConsistentID.py:537-540, 560-571):
+//   eps   = eps_u + g * (eps_c - eps_u)                      eps rows: [2B*HW, ld_eps], first 4 columns valid
+//   x0    = kx * x + ke * eps                                (kept for multistep solvers)
+//   x'    = cx * x + ce * eps + cp * x0_prev                 (DDIM / Euler / DPM-Solver++(2M) are all of this form)
+//   next UNet input (both CFG halves, NHWC, CP channels, zero padded) = x' * in_scale_next
+// coef[step] = {cx, ce, cp, kx, ke, in_scale_next, 0, 0}; step index read from device memory (CUDA-graph friendly).
+// Master latents x are fp32 [B, 4, HW] (NCHW); a 16-bit copy is written for the API surface.
+__global__ void __launch_bounds__(256)
+cfg_sched_step_kernel(const uint16_t* __restrict__ eps, int ld_eps, float* __restrict__ x, float* __restrict__ x0_prev,
+                      uint16_t* __restrict__ x16, uint16_t* __restrict__ next_in, int CP, int B, int HW, float guidance,
+                      const float* __restrict__ coef_table, const int* __restrict__ step_ptr, int bf) {
+  const float* cf = coef_table + 8 * (*step_ptr);
+  const float cx = cf[0], ce = cf[1], cp = cf[2], kx = cf[3], ke = cf[4], sc = cf[5];
+  const long long total = (long long)B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = int(i / HW), p = int(i % HW);
+    const uint2 eu = *reinterpret_cast<const uint2*>(eps + ((size_t)b * HW + p) * ld_eps);
+    const uint2 ec = *reinterpret_cast<const uint2*>(eps + ((size_t)(B + b) * HW + p) * ld_eps);
+    float2 u01 = unpack16(eu.x, bf), u23 = unpack16(eu.y, bf), c01 = unpack16(ec.x, bf), c23 = unpack16(ec.y, bf);
+    const float uu[4] = {u01.x, u01.y, u23.x, u23.y}, cc[4] = {c01.x, c01.y, c23.x, c23.y};
+    float nx[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) nx[k] = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const size_t o = ((size_t)b * 4 + ch) * HW + p;
+      const float e = uu[ch] + guidance * (cc[ch] - uu[ch]);
+      const float xv = x[o];
+      const float x0 = kx * xv + ke * e;
+      const float xn = cx * xv + ce * e + cp * x0_prev[o];
+      x0_prev[o] = x0;
+      x[o] = xn;
+      store16(x16, o, xn, bf);
+      nx[ch] = xn * sc;
+    }
+    if (next_in) {
+      const uint4 v = pack8(nx, bf);
+      uint4* d0 = reinterpret_cast<uint4*>(next_in + ((size_t)b * HW + p) * CP);
+      uint4* d1 = reinterpret_cast<uint4*>(next_in + ((size_t)(B + b) * HW + p) * CP);
+      d0[0] = v; d1[0] = v;                      // channels >= 8 stay zero (buffer zeroed once at allocation)
+    }
+  }
+}
+
+// first-step helper: fp32 master latents [B,4,HW] -> UNet input NHWC (both CFG halves), times in_scale of step 0
+__global__ void __launch_bounds__(256)
+latents_to_input_kernel(const float* __restrict__ x, uint16_t* __restrict__ next_in, int CP, int B, int HW,
+                        const float* __restrict__ coef_table, int bf) {
+  const float sc = coef_table[6];                // coef[0][6] = in_scale of step 0
+  const long long total = (long long)B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = int(i / HW), p = int(i % HW);
+    float nx[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) nx[k] = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) nx[ch] = x[((size_t)b * 4 + ch) * HW + p] * sc;
+    const uint4 v = pack8(nx, bf);
+    reinterpret_cast<uint4*>(next_in + ((size_t)b * HW + p) * CP)[0] = v;
+    reinterpret_cast<uint4*>(next_in + ((size_t)(B + b) * HW + p) * CP)[0] = v;
+  }
+}
+
+}  // namespace cid

@@ -1,0 +1,77 @@
+"""ctypes binding of libcidb200.so (include/cidb200.h).
+
+The library is the product: there is NO fallback.  If it has not been built
+(``python -c "import __graft_entry__ as g; g.build()"``) importing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcidb200.so")
+
+F16, BF16 = 0, 1
+EPI_STORE, EPI_GEGLU, EPI_QKV = 0, 1, 2
+
+
+class CidError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA library has not been built. Run __graft_entry__.build() "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU/eager fallback by design.")
+    return C.CDLL(LIB_PATH)
+
+
+_lib = _load()
+
+_vp, _ll, _i, _f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+_SIGS = {
+    "cid_version": ([], _i),
+    "cid_last_error": ([], C.c_char_p),
+    "cid_gemm_tile_n": ([_i, _i], _i),
+    "cid_gemm": ([_vp, _ll, _vp, _ll, _i, _i, _vp, _vp, _ll, _i, _i, _vp, _vp, _ll, _vp, _i, _ll, _i, _vp, _i, _i, _i, _i, _f, _i, _vp], _i),
+    "cid_conv3x3": ([_vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _ll, _vp, _ll, _f, _i, _vp], _i),
+    "cid_attn_self": ([_vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp], _i),
+    "cid_attn_cross": ([_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _f, _i, _vp], _i),
+    "cid_pack_cross_kv": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
+    "cid_gn_stats": ([_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp], _i),
+    "cid_gn_apply": ([_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _f, _i, _vp, _i, _vp], _i),
+    "cid_layernorm": ([_vp, _vp, _vp, _vp, _ll, _i, _f, _i, _vp], _i),
+    "cid_upsample2x": ([_vp, _vp, _i, _i, _i, _i, _vp], _i),
+    "cid_phase_split": ([_vp, _vp, _i, _i, _i, _i, _vp], _i),
+    "cid_nchw_to_nhwc_pad": ([_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp], _i),
+    "cid_rows_to_nchw": ([_vp, _i, _vp, _i, _i, _i, _vp], _i),
+    "cid_add_inplace": ([_vp, _vp, _ll, _i, _vp], _i),
+    "cid_timestep_embed": ([_vp, _i, _i, _i, _vp, _ll, _i, _i, _vp], _i),
+    "cid_skinny_linear": ([_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp], _i),
+    "cid_cfg_sched_step": ([_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _i, _vp], _i),
+    "cid_latents_to_input": ([_vp, _vp, _i, _i, _i, _vp, _i, _vp], _i),
+}
+EXPORTS = tuple(_SIGS)
+for _name, (_args, _res) in _SIGS.items():
+    _fn = getattr(_lib, _name)          # AttributeError here == header / library mismatch
+    _fn.argtypes, _fn.restype = _args, _res
+
+
+def last_error() -> str:
+    return _lib.cid_last_error().decode()
+
+
+def call(name, *args):
+    """Invoke a status-returning entry point; raise CidError with the library's message on failure."""
+    rc = getattr(_lib, name)(*args)
+    if rc != 0:
+        raise CidError(f"{name} failed ({rc}): {last_error()}")
+
+
+def version() -> int:
+    return _lib.cid_version()
+
+
+def gemm_tile_n(n: int, epi: int) -> int:
+    return _lib.cid_gemm_tile_n(n, epi)

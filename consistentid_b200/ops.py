@@ -1,0 +1,131 @@
+"""Thin torch-tensor wrappers over the C ABI (device memory + current stream come from PyTorch; the arithmetic
+is libcidb200.so).  Activations: 16-bit, row-major [rows, C] (== NHWC).  Every op launches on
+``torch.cuda.current_stream()`` and is CUDA-graph capturable."""
+from __future__ import annotations
+
+import torch
+
+from . import lib
+from .lib import EPI_GEGLU, EPI_QKV, EPI_STORE, call
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float16:
+        return lib.F16
+    if t.dtype == torch.bfloat16:
+        return lib.BF16
+    raise TypeError(f"cidb200 kernels compute in fp16/bf16, got {t.dtype}")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, name):
+    if t is not None and not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor")
+
+
+def gemm(a, w, out, bias=None, residual=None, rowbias=None, rows_per_group=1, a2=None, epi=EPI_STORE, vt=None,
+         n_split=0, heads=0, hdim=0, ntok=0, out_scale=1.0):
+    """out[M, :] = epi([a | a2] @ w.T + bias + rowbias[row // rows_per_group] + residual) * out_scale.
+    a: [M, K1] (last-dim contiguous, row pitch a.stride(0)); w: [N, K1+K2] contiguous."""
+    _chk(a, "a")
+    M, K1 = a.shape
+    K2 = 0 if a2 is None else a2.shape[1]
+    N = w.shape[0]
+    assert w.shape[1] == K1 + K2 and w.is_contiguous()
+    assert a.stride(1) == 1 and out.stride(1) == 1
+    call("cid_gemm", _p(a), a.stride(0), _p(a2), 0 if a2 is None else a2.stride(0), K1, K2, _p(w), _p(out), out.stride(0),
+         M, N, _p(bias), _p(residual), 0 if residual is None else residual.stride(0), _p(rowbias), rows_per_group,
+         0 if rowbias is None else rowbias.stride(0), epi, _p(vt), n_split, heads, hdim, ntok, float(out_scale), _dt(a), _stream())
+    return out
+
+
+def conv3x3(x, w, out, NB, H, W, Cin, Cout, bias=None, residual=None, rowbias=None, stride2=False, out_scale=1.0):
+    """x: NHWC [NB,H,W,Cin] (or phase-split [NB,4,H,W,Cin] when stride2; H,W = output dims); w: [Cout, 9*Cin];
+    out: [NB*H*W, >=Cout] rows."""
+    call("cid_conv3x3", _p(x), _p(w), _p(out), out.stride(0), NB, H, W, Cin, Cout, 1 if stride2 else 0, _p(bias), _p(residual),
+         0 if residual is None else residual.stride(0), _p(rowbias), 0 if rowbias is None else rowbias.stride(0),
+         float(out_scale), _dt(x), _stream())
+    return out
+
+
+def attn_self(q, k, vt, out, B, H, N, d):
+    """q,k: views [B*N, >=H*d] (row pitch = stride(0)); vt: [B*H, d, N]; out: [B*N, H*d]."""
+    call("cid_attn_self", _p(q), q.stride(0), _p(k), k.stride(0), _p(vt), _p(out), out.stride(0), B, H, N, d, _dt(q), _stream())
+    return out
+
+
+def attn_cross(q, k_cat, vt_cat, out, B, H, N, d, n_text, n_ip, ip_scale):
+    call("cid_attn_cross", _p(q), q.stride(0), _p(k_cat), _p(vt_cat), _p(out), out.stride(0), B, H, N, d, n_text, n_ip,
+         float(ip_scale), _dt(q), _stream())
+    return out
+
+
+def pack_cross_kv(k_text, v_text, k_ip, v_ip, k_cat, vt_cat, B, C, heads, n_text, n_ip):
+    call("cid_pack_cross_kv", _p(k_text), _p(v_text), _p(k_ip), _p(v_ip), _p(k_cat), _p(vt_cat), B, C, heads, n_text, n_ip, _stream())
+
+
+def gn_stats(x1, C1, x2, C2, NB, HW, groups, sums):
+    call("cid_gn_stats", _p(x1), C1, _p(x2), C2, NB, HW, groups, _p(sums), _dt(x1), _stream())
+
+
+def gn_apply(x1, C1, x2, C2, NB, HW, groups, sums, gamma, beta, eps, silu, out):
+    call("cid_gn_apply", _p(x1), C1, _p(x2), C2, NB, HW, groups, _p(sums), _p(gamma), _p(beta), float(eps), 1 if silu else 0,
+         _p(out), _dt(x1), _stream())
+    return out
+
+
+def layernorm(x, gamma, beta, out, rows, C, eps=1e-5):
+    call("cid_layernorm", _p(x), _p(gamma), _p(beta), _p(out), rows, C, float(eps), _dt(x), _stream())
+    return out
+
+
+def upsample2x(x, out, NB, H, W, C):
+    call("cid_upsample2x", _p(x), _p(out), NB, H, W, C, _stream())
+    return out
+
+
+def phase_split(x, out, NB, H, W, C):
+    call("cid_phase_split", _p(x), _p(out), NB, H, W, C, _stream())
+    return out
+
+
+def nchw_to_nhwc_pad(x, out, NB, Cin, HW, CP, scale_dev=None):
+    call("cid_nchw_to_nhwc_pad", _p(x), _p(out), NB, Cin, HW, CP, _p(scale_dev), _dt(x), _stream())
+    return out
+
+
+def rows_to_nchw(x, ld, out, NB, Cout, HW):
+    call("cid_rows_to_nchw", _p(x), ld, _p(out), NB, Cout, HW, _stream())
+    return out
+
+
+def add_inplace(y, x):
+    call("cid_add_inplace", _p(y), _p(x), y.numel(), _dt(y), _stream())
+    return y
+
+
+def timestep_embed(t_dev, t_stride, rows, dim, out, ld, col0=0):
+    call("cid_timestep_embed", _p(t_dev), t_stride, rows, dim, _p(out), ld, col0, _dt(out), _stream())
+    return out
+
+
+def skinny_linear(x, w, bias, out, M, N, K, silu_in=False, accumulate=False):
+    call("cid_skinny_linear", _p(x), x.stride(0), _p(w), _p(bias), _p(out), out.stride(0), M, N, K, 1 if silu_in else 0,
+         1 if accumulate else 0, _dt(x), _stream())
+    return out
+
+
+def cfg_sched_step(eps, ld_eps, x, x0_prev, x16, next_in, CP, B, HW, guidance, coef_table, step_dev):
+    call("cid_cfg_sched_step", _p(eps), ld_eps, _p(x), _p(x0_prev), _p(x16), _p(next_in), CP, B, HW, float(guidance),
+         _p(coef_table), _p(step_dev), _dt(eps), _stream())
+
+
+def latents_to_input(x, next_in, CP, B, HW, coef_table):
+    call("cid_latents_to_input", _p(x), _p(next_in), CP, B, HW, _p(coef_table), _dt(next_in), _stream())

@@ -1,0 +1,35 @@
+"""Weight preparation for the B200 engine: LoRA folding, GEGLU tile interleave, conv weight re-layout,
+checkpoint-format handling (adapter_modules positional keys, pipline_StableDiffusion_ConsistentID.py:134-144).
+Pure tensor re-arrangement done once at load time (any device)."""
+from __future__ import annotations
+
+import torch
+
+
+def fold_lora(w: torch.Tensor, down: torch.Tensor, up: torch.Tensor, lora_scale: float = 1.0,
+              network_alpha=None) -> torch.Tensor:
+    """W' = W + lora_scale * (alpha/rank) * up @ down, in fp32, cast back once.
+    Exact restatement of ``attn.to_q(x) + lora_scale * to_q_lora(x)`` (attention.py:138, 236) up to 16-bit rounding order."""
+    rank = down.shape[0]
+    s = lora_scale * ((network_alpha / rank) if network_alpha is not None else 1.0)
+    return (w.float() + s * (up.float() @ down.float())).to(w.dtype)
+
+
+def interleave_geglu(w: torch.Tensor, b: torch.Tensor | None, tile_n: int):
+    """Re-order the rows of GEGLU's ``proj`` ([2*inner, K]; first half = value, second = gate) so that each GEMM N-tile of
+    width ``tile_n`` holds ``tile_n/2`` value rows followed by the matching ``tile_n/2`` gate rows."""
+    inner = w.shape[0] // 2
+    half = tile_n // 2
+    assert inner % half == 0, (inner, half)
+    idx = torch.arange(inner, device=w.device).reshape(-1, half)
+    order = torch.cat([idx, idx + inner], dim=1).reshape(-1)
+    return w[order].contiguous(), (None if b is None else b[order].contiguous())
+
+
+def pack_conv3x3(w: torch.Tensor, cin_pad: int | None = None) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> [Cout, 9 * Cin_pad] with K index = (ky*3 + kx) * Cin_pad + c (zero padded channels)."""
+    cout, cin = w.shape[:2]
+    cp = cin_pad or cin
+    out = torch.zeros((cout, 3, 3, cp), dtype=w.dtype, device=w.device)
+    out[..., :cin] = w.permute(0, 2, 3, 1)
+    return out.reshape(cout, 9 * cp).contiguous()

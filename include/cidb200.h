@@ -1,0 +1,90 @@
+/* cidb200 - C ABI of the B200-native ConsistentID denoising hot path (libcidb200.so).
+ *
+ * The reference has NO C ABI for this path: its arithmetic is reached through Python objects
+ *   - diffusers AttnProcessor protocol   attention.py:110-117 / :207-215 (processor __call__)
+ *   - unet(...).sample                   pipline_StableDiffusion_ConsistentID.py:552-557,
+ *                                        pipline_StableDiffusionXL_ConsistentID.py:634-641
+ *   - scheduler.scale_model_input/step   pipline_StableDiffusion_ConsistentID.py:540, 569-571
+ * and its only native binding is a pybind11 module of dead code (models/BiSeNet/modules/src/inplace_abn.cpp:86-95).
+ * This header therefore DEFINES the boundary a replacement binds to; each entry point names the reference
+ * lines whose arithmetic it replaces.  INTEGRATION.md shows the ctypes stub on the reference side.
+ *
+ * Conventions: every pointer is a DEVICE pointer (16-byte aligned) unless stated otherwise; activations are
+ * 16-bit (dtype 0 = fp16, 1 = bf16), row-major [rows, channels] == NHWC; `ld*`/pitches are in ELEMENTS;
+ * `stream` is a cudaStream_t.  Functions never allocate, free or synchronise; they return 0 on success or a
+ * negative cid_status and set a thread-local message readable with cid_last_error().  All of them are
+ * CUDA-graph capturable.
+ */
+#ifndef CIDB200_H
+#define CIDB200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { CID_OK = 0, CID_ERR_ARG = -1, CID_ERR_CUDA = -2, CID_ERR_UNSUPPORTED = -3, CID_ERR_DRIVER = -4 } cid_status;
+typedef enum { CID_F16 = 0, CID_BF16 = 1 } cid_dtype;
+typedef enum { CID_EPI_STORE = 0, CID_EPI_GEGLU = 1, CID_EPI_QKV = 2 } cid_epilogue;
+
+int cid_version(void);
+const char* cid_last_error(void);
+/* N-tile width the GEMM will use for (N, epilogue): GEGLU weights must be row-interleaved per tile of this width. */
+int cid_gemm_tile_n(int N, int epi);
+
+/* C[M,N] = epi( [A | A2][M, K1+K2] . B[N, K1+K2]^T + bias[N] + rowbias[row / rows_per_group, N] + residual[M,N] ) * out_scale
+ * Replaces: attn.to_q/to_k/to_v/to_out (+ LoRA folded) attention.py:138-146,162,236-250,282; BasicTransformerBlock
+ * GEGLU / FF linears, Transformer2D proj_in/out, ResnetBlock2D 1x1 conv_shortcut (diffusers 0.23).
+ *   epi = GEGLU : B rows interleaved per tile (value half | gate half); writes C[M, N/2] = v * gelu(g).
+ *   epi = QKV   : columns >= n_split are V and are written TRANSPOSED to Vt[(row/ntok)*heads + h, dd, row%ntok]. */
+int cid_gemm(const void* A, long long lda, const void* A2, long long lda2, int K1, int K2, const void* B,
+             void* C, long long ldc, int M, int N, const void* bias, const void* residual, long long ldr,
+             const void* rowbias, int rows_per_group, long long ld_rowbias, int epi, void* Vt, int n_split, int heads,
+             int hdim, int ntok, float out_scale, int dtype, void* stream);
+
+/* 3x3 convolution, padding 1, as implicit GEMM over NHWC.  X: [NB,H,W,Cin] (stride 1) or the phase-split copy
+ * [NB,4,H,W,Cin] of a [NB,2H,2W,Cin] tensor (stride2 = 1; H,W are OUTPUT dims).  Wt: [Cout, 9*Cin] = (ky,kx,c) order.
+ * Y[NB*H*W, ldy].  Replaces ResnetBlock2D.conv1/conv2, Downsample2D.conv, Upsample2D.conv, conv_in, conv_out. */
+int cid_conv3x3(const void* X, const void* Wt, void* Y, long long ldy, int NB, int H, int W, int Cin, int Cout,
+                int stride2, const void* bias, const void* residual, long long ldr, const void* rowbias,
+                long long ld_rowbias, float out_scale, int dtype, void* stream);
+
+/* softmax(Q K^T / sqrt(d)) V per (sample, head).  Q,K: [B,N,H,d] views with row pitch q_pitch/k_pitch;
+ * Vt: [B*H, d, N] (keys contiguous); O: [B,N,H*d] pitch ldo.  Replaces attention.py:152-159. */
+int cid_attn_self(const void* Q, long long q_pitch, const void* K, long long k_pitch, const void* Vt, void* O,
+                  long long ldo, int B, int H, int N, int d, int dtype, void* stream);
+
+/* Decoupled text + id cross-attention: O = softmax(Q Kt^T) Vt + ip_scale * softmax(Q Ki^T) Vi, with
+ * Kcat [B, 96, H*d] (rows [0,n_text) text, [80,80+n_ip) id, others zero) and Vtcat [B*H, d, 96].
+ * Replaces attention.py:259-279. */
+int cid_attn_cross(const void* Q, long long q_pitch, const void* Kcat, const void* Vtcat, void* O, long long ldo,
+                   int B, int H, int N, int d, int n_text, int n_ip, float ip_scale, int dtype, void* stream);
+int cid_pack_cross_kv(const void* k_text, const void* v_text, const void* k_ip, const void* v_ip, void* k_cat,
+                      void* vt_cat, int B, int C, int heads, int n_text, int n_ip, void* stream);
+
+/* GroupNorm over cat([x1 (C1), x2 (C2)]) NHWC: stats into sums[NB, groups, 2] (fp32; zeroed by the call), then
+ * y = [silu](gn(x)).  Replaces ResnetBlock2D.norm1/norm2 + nonlinearity, Transformer2D.norm, conv_norm_out + conv_act. */
+int cid_gn_stats(const void* x1, int C1, const void* x2, int C2, int NB, int HW, int groups, float* sums, int dtype, void* stream);
+int cid_gn_apply(const void* x1, int C1, const void* x2, int C2, int NB, int HW, int groups, const float* sums,
+                 const void* gamma, const void* beta, float eps, int silu, void* y, int dtype, void* stream);
+int cid_layernorm(const void* x, const void* gamma, const void* beta, void* y, long long rows, int C, float eps, int dtype, void* stream);
+int cid_upsample2x(const void* x, void* y, int NB, int H, int W, int C, void* stream);
+int cid_phase_split(const void* x, void* y, int NB, int H, int W, int C, void* stream);
+int cid_nchw_to_nhwc_pad(const void* x, void* y, int NB, int Cin, int HW, int CP, const float* scale_dev, int dtype, void* stream);
+int cid_rows_to_nchw(const void* x, int ld, void* y, int NB, int Cout, int HW, void* stream);
+int cid_add_inplace(void* y, const void* x, long long n_elems, int dtype, void* stream);
+
+/* diffusers get_timestep_embedding(flip_sin_to_cos=True, freq_shift=0); t read from device memory. */
+int cid_timestep_embed(const float* t_dev, int t_stride, int rows, int dim, void* out, long long ld, int col0, int dtype, void* stream);
+/* y[M,N] (+)= act(x)[M,K] . W[N,K]^T + b for M <= 64 (time_embedding, add_embedding, all time_emb_proj at once). */
+int cid_skinny_linear(const void* x, long long ldx, const void* W, const void* bias, void* y, long long ldy, int M, int N,
+                      int K, int silu_in, int accumulate, int dtype, void* stream);
+
+/* Fused CFG combine + scheduler step + next-step UNet input (pipline_StableDiffusion_ConsistentID.py:537-540,560-571).
+ * coef_table: device [steps, 8] fp32 rows {cx, ce, cp, kx, ke, in_scale_next, in_scale_this, 0}; step index from device. */
+int cid_cfg_sched_step(const void* eps, int ld_eps, float* x, float* x0_prev, void* x16, void* next_in, int CP, int B,
+                       int HW, float guidance, const float* coef_table, const int* step_dev, int dtype, void* stream);
+int cid_latents_to_input(const float* x, void* next_in, int CP, int B, int HW, const float* coef_table, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,362 @@
+"""Per-kernel parity checks of libcidb200.so against plain PyTorch fp32 references (GPU only).
+
+Used by tests/test_kernels_gpu.py (pytest -m gpu) and by tools/run_battery.py, which runs every check in its own
+subprocess (a device-side trap poisons the CUDA context) and writes a JSON report with error maps.
+Each check returns a dict {name, ok, max_err, ref_max, tol, ...}.
+"""
+from __future__ import annotations
+
+import json
+import math
+import sys
+
+import torch
+import torch.nn.functional as F
+
+DEV = "cuda"
+
+
+def _ops():
+    from consistentid_b200 import ops
+    return ops
+
+
+def _rand(shape, dtype, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+def _report(name, got, ref, tol_rel=None, extra=None):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    ref_max = ref.abs().max().item()
+    max_err = err.max().item() if err.numel() else 0.0
+    bad = not math.isfinite(max_err)
+    tol = (tol_rel or 1e-2) * max(ref_max, 1e-6)
+    out = {"name": name, "ok": (not bad) and max_err <= tol, "max_err": max_err, "ref_max": ref_max, "tol": tol,
+           "mean_err": err.mean().item() if err.numel() else 0.0, "nan": int(torch.isnan(got).sum().item())}
+    if not out["ok"] and err.ndim == 2:
+        # error map: which 32-row x 16-col blocks are wrong (layout / descriptor bugs show up as patterns)
+        R, Cc = err.shape
+        rb, cb = min(R, 128), min(Cc, 160)
+        e = err[:rb, :cb]
+        blk = e.reshape(rb // 8 if rb % 8 == 0 else 1, -1, e.shape[1]).amax(1) if rb % 8 == 0 else e
+        out["bad_rows_first"] = [int(i) for i in torch.nonzero(err.amax(1) > tol)[:16].flatten().tolist()]
+        out["bad_cols_first"] = [int(i) for i in torch.nonzero(err.amax(0) > tol)[:16].flatten().tolist()]
+        out["n_bad_rows"] = int((err.amax(1) > tol).sum().item())
+        out["n_bad_cols"] = int((err.amax(0) > tol).sum().item())
+        out["sample_got"] = got[:2, :8].tolist()
+        out["sample_ref"] = ref[:2, :8].tolist()
+    if extra:
+        out.update(extra)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+def check_gemm(M=256, N=320, K=320, dtype=torch.float16, bias=True, residual=False, rowbias=False, K2=0, seed=0):
+    ops = _ops()
+    a = _rand((M, K), dtype, seed)
+    a2 = _rand((M, K2), dtype, seed + 5) if K2 else None
+    w = _rand((N, K + K2), dtype, seed + 1, (K + K2) ** -0.5)
+    b = _rand((N,), dtype, seed + 2) if bias else None
+    r = _rand((M, N), dtype, seed + 3) if residual else None
+    rpg = 64
+    rb = _rand(((M + rpg - 1) // rpg, N), dtype, seed + 4) if rowbias else None
+    out = torch.full((M, N), float("nan"), dtype=dtype, device=DEV)
+    ops.gemm(a, w, out, bias=b, residual=r, rowbias=rb, rows_per_group=rpg, a2=a2)
+    torch.cuda.synchronize()
+    af = a.float() if a2 is None else torch.cat([a.float(), a2.float()], 1)
+    ref = af @ w.float().T
+    if bias: ref = ref + b.float()
+    if rowbias: ref = ref + rb.float().repeat_interleave(rpg, 0)[:M]
+    if residual: ref = ref + r.float()
+    return _report(f"gemm M{M} N{N} K{K}+{K2} {str(dtype)[6:]} b{int(bias)} r{int(residual)} rb{int(rowbias)}", out, ref, 8e-3)
+
+
+def check_gemm_geglu(M=256, C=320, dtype=torch.float16, seed=0):
+    ops = _ops()
+    from consistentid_b200 import lib
+    from consistentid_b200.weights import interleave_geglu
+    N = 8 * C
+    a = _rand((M, C), dtype, seed)
+    w = _rand((N, C), dtype, seed + 1, C ** -0.5)
+    b = _rand((N,), dtype, seed + 2, 0.1)
+    bn = lib.gemm_tile_n(N, lib.EPI_GEGLU)
+    wi, bi = interleave_geglu(w, b, bn)
+    out = torch.full((M, N // 2), float("nan"), dtype=dtype, device=DEV)
+    ops.gemm(a, wi, out, bias=bi, epi=lib.EPI_GEGLU)
+    torch.cuda.synchronize()
+    proj = (a.float() @ w.float().T + b.float()).to(dtype).float()
+    v, g = proj.chunk(2, -1)
+    ref = v * F.gelu(g)
+    return _report(f"gemm_geglu M{M} C{C} bn{bn} {str(dtype)[6:]}", out, ref, 8e-3)
+
+
+def check_gemm_qkv(B=2, ntok=128, C=320, heads=8, dtype=torch.float16, seed=0):
+    ops = _ops()
+    from consistentid_b200 import lib
+    M, d = B * ntok, C // heads
+    a = _rand((M, C), dtype, seed)
+    w = _rand((3 * C, C), dtype, seed + 1, C ** -0.5)
+    qk = torch.full((M, 2 * C), float("nan"), dtype=dtype, device=DEV)
+    vt = torch.full((B * heads, d, ntok), float("nan"), dtype=dtype, device=DEV)
+    ops.gemm(a, w, qk, epi=lib.EPI_QKV, vt=vt, n_split=2 * C, heads=heads, hdim=d, ntok=ntok)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().T
+    r1 = _report(f"gemm_qkv(QK) B{B} n{ntok} C{C} h{heads}", qk, ref[:, :2 * C], 8e-3)
+    vref = ref[:, 2 * C:].reshape(B, ntok, heads, d).permute(0, 2, 3, 1).reshape(B * heads, d, ntok)
+    r2 = _report(f"gemm_qkv(Vt) B{B} n{ntok} C{C} h{heads}", vt.reshape(B * heads * d, ntok), vref.reshape(B * heads * d, ntok), 8e-3)
+    r1["ok"] = r1["ok"] and r2["ok"]
+    r1["vt"] = r2
+    return r1
+
+
+# ------------------------------------------------------------------------------------------------ conv
+def _conv_weight_pack(w):  # [Cout, Cin, 3, 3] -> [Cout, 9*Cin] (ky, kx, c)
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+
+def check_conv(NB=2, H=32, W=32, Cin=128, Cout=320, dtype=torch.float16, stride2=False, bias=True, residual=False,
+               rowbias=False, seed=0):
+    ops = _ops()
+    Hi, Wi = (2 * H, 2 * W) if stride2 else (H, W)
+    x = _rand((NB, Hi, Wi, Cin), dtype, seed)                       # NHWC
+    w = _rand((Cout, Cin, 3, 3), dtype, seed + 1, (9 * Cin) ** -0.5)
+    b = _rand((Cout,), dtype, seed + 2) if bias else None
+    r = _rand((NB * H * W, Cout), dtype, seed + 3) if residual else None
+    rb = _rand((NB, Cout), dtype, seed + 4) if rowbias else None
+    out = torch.full((NB * H * W, Cout), float("nan"), dtype=dtype, device=DEV)
+    xin = x
+    if stride2:
+        xin = torch.empty((NB, 4, H, W, Cin), dtype=dtype, device=DEV)
+        ops.phase_split(x, xin, NB, Hi, Wi, Cin)
+    ops.conv3x3(xin, _conv_weight_pack(w), out, NB, H, W, Cin, Cout, bias=b, residual=r, rowbias=rb, stride2=stride2)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), None if b is None else b.float(), stride=2 if stride2 else 1, padding=1)
+    if rowbias: ref = ref + rb.float()[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1).reshape(NB * H * W, Cout)
+    if residual: ref = ref + r.float()
+    return _report(f"conv NB{NB} {H}x{W} {Cin}->{Cout} s{2 if stride2 else 1} {str(dtype)[6:]} b{int(bias)} r{int(residual)} rb{int(rowbias)}",
+                   out, ref, 8e-3)
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def check_attn_self(B=2, H=2, N=256, d=64, dtype=torch.float16, seed=0):
+    ops = _ops()
+    C = H * d
+    qk = _rand((B * N, 2 * C), dtype, seed)
+    v = _rand((B, N, H, d), dtype, seed + 1)
+    vt = v.permute(0, 2, 3, 1).reshape(B * H, d, N).contiguous()
+    out = torch.full((B * N, C), float("nan"), dtype=dtype, device=DEV)
+    ops.attn_self(qk[:, :C], qk[:, C:], vt, out, B, H, N, d)
+    torch.cuda.synchronize()
+    q = qk[:, :C].float().reshape(B, N, H, d).transpose(1, 2)
+    k = qk[:, C:].float().reshape(B, N, H, d).transpose(1, 2)
+    p = torch.softmax(q @ k.transpose(-1, -2) * d ** -0.5, -1)
+    ref = (p @ v.float().transpose(1, 2)).transpose(1, 2).reshape(B * N, C)
+    return _report(f"attn_self B{B} H{H} N{N} d{d} {str(dtype)[6:]}", out, ref, 1e-2)
+
+
+def check_attn_cross(B=2, H=2, N=256, d=64, dtype=torch.float16, n_text=77, n_ip=4, ip_scale=1.0, seed=0):
+    ops = _ops()
+    C = H * d
+    q = _rand((B * N, C), dtype, seed)
+    kt, vt_ = _rand((B * n_text, C), dtype, seed + 1), _rand((B * n_text, C), dtype, seed + 2)
+    ki, vi = _rand((B * n_ip, C), dtype, seed + 3), _rand((B * n_ip, C), dtype, seed + 4)
+    k_cat = torch.full((B, 96, C), float("nan"), dtype=dtype, device=DEV)
+    vt_cat = torch.full((B * H, d, 96), float("nan"), dtype=dtype, device=DEV)
+    ops.pack_cross_kv(kt, vt_, ki, vi, k_cat, vt_cat, B, C, H, n_text, n_ip)
+    out = torch.full((B * N, C), float("nan"), dtype=dtype, device=DEV)
+    ops.attn_cross(q, k_cat, vt_cat, out, B, H, N, d, n_text, n_ip, ip_scale)
+    torch.cuda.synchronize()
+
+    def heads(t, n):
+        return t.float().reshape(B, n, H, d).transpose(1, 2)
+    qh = heads(q, N)
+    o1 = torch.softmax(qh @ heads(kt, n_text).transpose(-1, -2) * d ** -0.5, -1) @ heads(vt_, n_text)
+    o2 = torch.softmax(qh @ heads(ki, n_ip).transpose(-1, -2) * d ** -0.5, -1) @ heads(vi, n_ip)
+    ref = (o1 + ip_scale * o2).transpose(1, 2).reshape(B * N, C)
+    return _report(f"attn_cross B{B} H{H} N{N} d{d} {str(dtype)[6:]} s{ip_scale}", out, ref, 1e-2)
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+def check_groupnorm(NB=2, HW=256, C1=320, C2=0, groups=32, silu=True, dtype=torch.float16, eps=1e-5, seed=0):
+    ops = _ops()
+    x1 = _rand((NB, HW, C1), dtype, seed) + 0.5
+    x2 = (_rand((NB, HW, C2), dtype, seed + 1) * 2 - 0.3) if C2 else None
+    C = C1 + C2
+    ga, be = _rand((C,), dtype, seed + 2) + 1, _rand((C,), dtype, seed + 3)
+    sums = torch.empty((NB, groups, 2), dtype=torch.float32, device=DEV)
+    out = torch.full((NB, HW, C), float("nan"), dtype=dtype, device=DEV)
+    ops.gn_stats(x1, C1, x2, C2, NB, HW, groups, sums)
+    ops.gn_apply(x1, C1, x2, C2, NB, HW, groups, sums, ga, be, eps, silu, out)
+    torch.cuda.synchronize()
+    x = x1.float() if x2 is None else torch.cat([x1.float(), x2.float()], -1)
+    ref = F.group_norm(x.permute(0, 2, 1), groups, ga.float(), be.float(), eps)
+    if silu: ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1)
+    return _report(f"groupnorm NB{NB} HW{HW} C{C1}+{C2} silu{int(silu)} {str(dtype)[6:]}", out.reshape(-1, C), ref.reshape(-1, C), 5e-3)
+
+
+def check_layernorm(rows=1000, C=320, dtype=torch.float16, seed=0):
+    ops = _ops()
+    x = _rand((rows, C), dtype, seed) * 2 + 0.3
+    ga, be = _rand((C,), dtype, seed + 2) + 1, _rand((C,), dtype, seed + 3)
+    out = torch.full((rows, C), float("nan"), dtype=dtype, device=DEV)
+    ops.layernorm(x, ga, be, out, rows, C)
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x.float(), (C,), ga.float(), be.float(), 1e-5)
+    return _report(f"layernorm rows{rows} C{C} {str(dtype)[6:]}", out, ref, 5e-3)
+
+
+def check_resample(dtype=torch.float16, seed=0):
+    ops = _ops()
+    NB, H, W, C = 2, 8, 12, 64
+    x = _rand((NB, H, W, C), dtype, seed)
+    up = torch.empty((NB, 2 * H, 2 * W, C), dtype=dtype, device=DEV)
+    ops.upsample2x(x, up, NB, H, W, C)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    r = _report("upsample2x", up.reshape(-1, C), ref.reshape(-1, C), 1e-6)
+    ps = torch.empty((NB, 4, H // 2, W // 2, C), dtype=dtype, device=DEV)
+    ops.phase_split(x, ps, NB, H, W, C)
+    refp = torch.stack([x[:, py::2, px::2] for py in (0, 1) for px in (0, 1)], 1)
+    r2 = _report("phase_split", ps.reshape(-1, C), refp.reshape(-1, C), 1e-6)
+    lat = _rand((NB, 4, H, W), dtype, seed + 1)
+    nh = torch.full((NB, H * W, 64), float("nan"), dtype=dtype, device=DEV)
+    ops.nchw_to_nhwc_pad(lat, nh, NB, 4, H * W, 64)
+    refn = torch.zeros((NB, H * W, 64), device=DEV)
+    refn[:, :, :4] = lat.float().reshape(NB, 4, H * W).permute(0, 2, 1)
+    r3 = _report("nchw_to_nhwc_pad", nh.reshape(-1, 64), refn.reshape(-1, 64), 1e-6)
+    back = torch.empty((NB, 4, H, W), dtype=dtype, device=DEV)
+    ops.rows_to_nchw(nh.reshape(-1, 64), 64, back, NB, 4, H * W)
+    r4 = _report("rows_to_nchw", back.reshape(NB * 4, -1), lat.reshape(NB * 4, -1), 1e-6)
+    y = _rand((NB, 64), dtype, seed + 2); yy = y.clone()
+    z = _rand((NB, 64), dtype, seed + 3)
+    ops.add_inplace(yy, z)
+    r5 = _report("add_inplace", yy, (y.float() + z.float()).to(dtype), 1e-6)
+    torch.cuda.synchronize()
+    r["ok"] = all(t["ok"] for t in (r, r2, r3, r4, r5))
+    r["sub"] = [r2, r3, r4, r5]
+    return r
+
+
+def check_time_embed(dtype=torch.float16):
+    ops = _ops()
+    rows, dim = 4, 320
+    t = torch.tensor([981.0], device=DEV)
+    out = torch.empty((rows, dim), dtype=dtype, device=DEV)
+    ops.timestep_embed(t, 0, rows, dim, out, dim)
+    torch.cuda.synchronize()
+    half = dim // 2
+    f = torch.exp(-math.log(10000) * torch.arange(half, device=DEV).float() / half)
+    e = t[:, None] * f[None]
+    ref = torch.cat([torch.cos(e), torch.sin(e)], -1).expand(rows, -1)
+    return _report("timestep_embed", out, ref, 2e-3)
+
+
+def check_skinny(M=16, N=1280, K=320, dtype=torch.float16, silu_in=True, seed=0):
+    ops = _ops()
+    x = _rand((M, K), dtype, seed)
+    w = _rand((N, K), dtype, seed + 1, K ** -0.5)
+    b = _rand((N,), dtype, seed + 2)
+    out = _rand((M, N), dtype, seed + 3)
+    prev = out.clone()
+    ops.skinny_linear(x, w, b, out, M, N, K, silu_in=silu_in, accumulate=True)
+    torch.cuda.synchronize()
+    xf = F.silu(x.float()).to(dtype).float() if silu_in else x.float()
+    ref = xf @ w.float().T + b.float() + prev.float()
+    return _report(f"skinny M{M} N{N} K{K} silu{int(silu_in)}", out, ref, 5e-3)
+
+
+def check_cfg_step(dtype=torch.float16, seed=0):
+    ops = _ops()
+    B, HW, CP = 3, 64, 64
+    eps = _rand((2 * B * HW, 4), dtype, seed)
+    x = _rand((B, 4, HW), torch.float32, seed + 1)
+    x0p = _rand((B, 4, HW), torch.float32, seed + 2)
+    coef = torch.tensor([[0, 0, 0, 0, 0, 0, 0, 0], [0.9, -0.3, 0.2, 1.1, -0.5, 0.7, 1.0, 0]], dtype=torch.float32, device=DEV)
+    step = torch.tensor([1], dtype=torch.int32, device=DEV)
+    xs, x0s = x.clone(), x0p.clone()
+    x16 = torch.empty((B, 4, HW), dtype=dtype, device=DEV)
+    nxt = torch.zeros((2 * B * HW, CP), dtype=dtype, device=DEV)
+    g = 5.0
+    ops.cfg_sched_step(eps, 4, xs, x0s, x16, nxt, CP, B, HW, g, coef, step)
+    torch.cuda.synchronize()
+    e = eps.float().reshape(2, B, HW, 4).permute(0, 1, 3, 2)
+    e = e[0] + g * (e[1] - e[0])
+    x0 = 1.1 * x - 0.5 * e
+    xn = 0.9 * x - 0.3 * e + 0.2 * x0p
+    r = _report("cfg_step(x)", xs.reshape(B * 4, HW), xn.reshape(B * 4, HW), 1e-5)
+    r2 = _report("cfg_step(x0)", x0s.reshape(B * 4, HW), x0.reshape(B * 4, HW), 1e-5)
+    refn = torch.zeros((2, B, HW, CP), device=DEV)
+    refn[:, :, :, :4] = (xn * 0.7).permute(0, 2, 1)[None]
+    r3 = _report("cfg_step(next_in)", nxt, refn.reshape(-1, CP), 2e-3)
+    r["ok"] = r["ok"] and r2["ok"] and r3["ok"]
+    r["sub"] = [r2, r3]
+    return r
+
+
+H16, B16 = torch.float16, torch.bfloat16
+CHECKS = {
+    # name: (fn, kwargs)
+    "gemm_basic": (check_gemm, dict(M=256, N=320, K=320)),
+    "gemm_k64": (check_gemm, dict(M=128, N=160, K=64, bias=False)),
+    "gemm_bf16": (check_gemm, dict(M=512, N=640, K=1280, dtype=B16, residual=True)),
+    "gemm_partial": (check_gemm, dict(M=200, N=100, K=128, residual=True, rowbias=True)),
+    "gemm_bn64": (check_gemm, dict(M=300, N=128, K=256)),
+    "gemm_bn16": (check_gemm, dict(M=256, N=4, K=320)),
+    "gemm_2src": (check_gemm, dict(M=256, N=320, K=640, K2=320)),
+    "gemm_big": (check_gemm, dict(M=4096, N=1280, K=2560, residual=True)),
+    "gemm_geglu160": (check_gemm_geglu, dict(M=256, C=320)),
+    "gemm_geglu64": (check_gemm_geglu, dict(M=128, C=64)),
+    "gemm_geglu_bf16": (check_gemm_geglu, dict(M=256, C=640, dtype=B16)),
+    "gemm_qkv40": (check_gemm_qkv, dict(B=2, ntok=128, C=320, heads=8)),
+    "gemm_qkv64": (check_gemm_qkv, dict(B=2, ntok=64, C=128, heads=2)),
+    "conv_32": (check_conv, dict(NB=2, H=32, W=32, Cin=128, Cout=320)),
+    "conv_64": (check_conv, dict(NB=1, H=64, W=64, Cin=64, Cout=160, rowbias=True)),
+    "conv_16": (check_conv, dict(NB=3, H=16, W=16, Cin=64, Cout=64, residual=True)),
+    "conv_8": (check_conv, dict(NB=5, H=8, W=8, Cin=192, Cout=320, rowbias=True, residual=True)),
+    "conv_128": (check_conv, dict(NB=1, H=128, W=128, Cin=64, Cout=160, dtype=B16)),
+    "conv_nonsq": (check_conv, dict(NB=2, H=24, W=16, Cin=64, Cout=160)),
+    "conv_w96": (check_conv, dict(NB=1, H=64, W=96, Cin=64, Cout=160)),
+    "conv_out4": (check_conv, dict(NB=2, H=32, W=32, Cin=320, Cout=4)),
+    "conv_s2": (check_conv, dict(NB=2, H=16, W=16, Cin=128, Cout=160, stride2=True)),
+    "conv_s2_64": (check_conv, dict(NB=1, H=32, W=32, Cin=64, Cout=320, stride2=True, dtype=B16)),
+    "attn_self_d64": (check_attn_self, dict(B=2, H=2, N=256, d=64)),
+    "attn_self_d40": (check_attn_self, dict(B=2, H=8, N=1024, d=40)),
+    "attn_self_d80": (check_attn_self, dict(B=1, H=4, N=256, d=80)),
+    "attn_self_d160": (check_attn_self, dict(B=2, H=2, N=256, d=160)),
+    "attn_self_d32": (check_attn_self, dict(B=2, H=2, N=128, d=32)),
+    "attn_self_n64": (check_attn_self, dict(B=3, H=2, N=64, d=160)),
+    "attn_self_n320": (check_attn_self, dict(B=1, H=2, N=320, d=64, dtype=B16)),
+    "attn_self_n4096": (check_attn_self, dict(B=1, H=2, N=4096, d=40)),
+    "attn_cross_d64": (check_attn_cross, dict(B=2, H=2, N=256, d=64)),
+    "attn_cross_d40": (check_attn_cross, dict(B=2, H=8, N=1024, d=40, ip_scale=0.7)),
+    "attn_cross_d80": (check_attn_cross, dict(B=1, H=4, N=200, d=80)),
+    "attn_cross_d160": (check_attn_cross, dict(B=2, H=2, N=64, d=160, dtype=B16)),
+    "attn_cross_d32": (check_attn_cross, dict(B=2, H=2, N=128, d=32)),
+    "gn_320": (check_groupnorm, dict(C1=320)),
+    "gn_concat": (check_groupnorm, dict(C1=640, C2=320, HW=1024)),
+    "gn_2560": (check_groupnorm, dict(C1=1280, C2=1280, HW=64, NB=3, dtype=B16)),
+    "gn_nosilu": (check_groupnorm, dict(C1=64, silu=False, eps=1e-6)),
+    "ln_320": (check_layernorm, dict(rows=1000, C=320)),
+    "ln_1280": (check_layernorm, dict(rows=77, C=1280, dtype=B16)),
+    "ln_64": (check_layernorm, dict(rows=33, C=64)),
+    "resample": (check_resample, {}),
+    "time_embed": (check_time_embed, {}),
+    "skinny": (check_skinny, dict(M=16, N=1280, K=320)),
+    "skinny_m40": (check_skinny, dict(M=40, N=333, K=2816, silu_in=False)),
+    "cfg_step": (check_cfg_step, {}),
+}
+
+
+def run(name):
+    fn, kw = CHECKS[name]
+    return fn(**kw)
+
+
+if __name__ == "__main__":
+    res = run(sys.argv[1])
+    print("RESULT " + json.dumps(res))
+    sys.exit(0 if res["ok"] else 1)
