@@ -384,4 +384,11 @@ int cid_latents_to_input(const float* x, void* next_in, int CP, int B, int HW, c
   return 0;
 }
 
+int cid_advance_step(int* step_dev, float* t_dev, const float* ts_table, int n, void* stream) {
+  if (!step_dev || !t_dev || !ts_table || n <= 0) return fail(CID_ERR_ARG, "cid_advance_step: bad arguments");
+  advance_step_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(step_dev, t_dev, ts_table, n);
+  CID_CHECK_LAUNCH("advance_step_kernel");
+  return 0;
+}
+
 }  // extern "C"

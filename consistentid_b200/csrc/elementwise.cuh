@@ -368,4 +368,13 @@ latents_to_input_kernel(const float* __restrict__ x, uint16_t* __restrict__ next
   }
 }
 
+// end-of-step bookkeeping inside the CUDA graph: step += 1; t = timesteps[step] (clamped)
+__global__ void advance_step_kernel(int* __restrict__ step, float* __restrict__ t_dev, const float* __restrict__ ts_table, int n) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const int s = *step + 1;
+    *step = s;
+    *t_dev = ts_table[s < n ? s : n - 1];
+  }
+}
+
 }  // namespace cid

@@ -129,3 +129,7 @@ def cfg_sched_step(eps, ld_eps, x, x0_prev, x16, next_in, CP, B, HW, guidance, c
 
 def latents_to_input(x, next_in, CP, B, HW, coef_table):
     call("cid_latents_to_input", _p(x), _p(next_in), CP, B, HW, _p(coef_table), _dt(next_in), _stream())
+
+
+def advance_step(step_dev, t_dev, ts_table, n):
+    call("cid_advance_step", _p(step_dev), _p(t_dev), _p(ts_table), n, _stream())

@@ -82,6 +82,8 @@ int cid_skinny_linear(const void* x, long long ldx, const void* W, const void* b
  * coef_table: device [steps, 8] fp32 rows {cx, ce, cp, kx, ke, in_scale_next, in_scale_this, 0}; step index from device. */
 int cid_cfg_sched_step(const void* eps, int ld_eps, float* x, float* x0_prev, void* x16, void* next_in, int CP, int B,
                        int HW, float guidance, const float* coef_table, const int* step_dev, int dtype, void* stream);
+/* in-graph step bookkeeping: *step_dev += 1; *t_dev = ts_table[min(*step_dev, n-1)] */
+int cid_advance_step(int* step_dev, float* t_dev, const float* ts_table, int n, void* stream);
 int cid_latents_to_input(const float* x, void* next_in, int CP, int B, int HW, const float* coef_table, int dtype, void* stream);
 
 #ifdef __cplusplus

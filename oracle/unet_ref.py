@@ -78,7 +78,7 @@ def tiny_config(kind="sd15") -> UNetConfig:
     multiples of 64 so the same kernels/tilings are exercised."""
     if kind == "sd15":
         return UNetConfig(block_out_channels=(64, 128, 256, 256), num_attention_heads=(2, 2, 4, 4),
-                          cross_attention_dim=128, sample_size=16, name="tiny_sd15")
+                          cross_attention_dim=128, sample_size=32, name="tiny_sd15")
     c = sdxl_config()
     c.block_out_channels = (64, 128, 256)
     c.transformer_layers_per_block = (1, 1, 2)
@@ -381,6 +381,7 @@ class UNet2DConditionRef(nn.Module):
         if cfg.addition_embed_type == "text_time":
             self.add_embedding = TimestepEmbedding(cfg.projection_class_embeddings_input_dim, cfg.time_embed_dim)
         self.down_blocks = nn.ModuleList()
+        self.up_blocks = nn.ModuleList()   # registered BEFORE mid_block, as in diffusers: attn_processors order = down, up, mid
         out_ch = boc[0]
         for i, t in enumerate(cfg.down_block_types):
             in_ch, out_ch = out_ch, boc[i]
@@ -388,7 +389,6 @@ class UNet2DConditionRef(nn.Module):
                                               cfg.transformer_layers_per_block[i], cfg.num_attention_heads[i],
                                               add_downsample=(i != len(boc) - 1)))
         self.mid_block = MidBlock(cfg, boc[-1], cfg.transformer_layers_per_block[-1], cfg.num_attention_heads[-1])
-        self.up_blocks = nn.ModuleList()
         rev = list(reversed(boc))
         rev_heads = list(reversed(cfg.num_attention_heads))
         rev_tf = list(reversed(cfg.transformer_layers_per_block))
