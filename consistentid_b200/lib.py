@@ -63,8 +63,13 @@ def last_error() -> str:
     return _lib.cid_last_error().decode()
 
 
+LAUNCHES = 0          # number of kernel-launching entry-point calls issued by this process (bench "gpu_launches")
+
+
 def call(name, *args):
     """Invoke a status-returning entry point; raise CidError with the library's message on failure."""
+    global LAUNCHES
+    LAUNCHES += 1
     rc = getattr(_lib, name)(*args)
     if rc != 0:
         raise CidError(f"{name} failed ({rc}): {last_error()}")

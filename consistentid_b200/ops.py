@@ -25,6 +25,39 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---- optional per-launch profiling (bench.py roofline pass): each tensor-core launch bracketed by CUDA events on the
+# launching (= torch current) stream, with its algorithmic FLOPs / bytes
+_PROFILE = None
+
+
+def profile_begin():
+    global _PROFILE
+    _PROFILE = []
+
+
+def profile_end():
+    """-> list of dicts {kind, flops, bytes, ms}"""
+    global _PROFILE
+    rec, _PROFILE = _PROFILE, None
+    torch.cuda.synchronize()
+    return [dict(kind=k, flops=f, bytes=b, ms=e0.elapsed_time(e1)) for k, f, b, e0, e1 in rec]
+
+
+class _prof:
+    def __init__(self, kind, flops, nbytes):
+        self.kind, self.flops, self.nbytes = kind, flops, nbytes
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True); self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if _PROFILE is not None:
+            self.e1.record()
+            _PROFILE.append((self.kind, self.flops, self.nbytes, self.e0, self.e1))
+
+
 def _chk(t, name):
     if t is not None and not t.is_cuda:
         raise ValueError(f"{name} must be a CUDA tensor")
@@ -40,30 +73,35 @@ def gemm(a, w, out, bias=None, residual=None, rowbias=None, rows_per_group=1, a2
     N = w.shape[0]
     assert w.shape[1] == K1 + K2 and w.is_contiguous()
     assert a.stride(1) == 1 and out.stride(1) == 1
-    call("cid_gemm", _p(a), a.stride(0), _p(a2), 0 if a2 is None else a2.stride(0), K1, K2, _p(w), _p(out), out.stride(0),
-         M, N, _p(bias), _p(residual), 0 if residual is None else residual.stride(0), _p(rowbias), rows_per_group,
-         0 if rowbias is None else rowbias.stride(0), epi, _p(vt), n_split, heads, hdim, ntok, float(out_scale), _dt(a), _stream())
+    with _prof("gemm", 2.0 * M * N * (K1 + K2), 2.0 * (M * (K1 + K2) + N * (K1 + K2) + M * N)):
+        call("cid_gemm", _p(a), a.stride(0), _p(a2), 0 if a2 is None else a2.stride(0), K1, K2, _p(w), _p(out), out.stride(0),
+             M, N, _p(bias), _p(residual), 0 if residual is None else residual.stride(0), _p(rowbias), rows_per_group,
+             0 if rowbias is None else rowbias.stride(0), epi, _p(vt), n_split, heads, hdim, ntok, float(out_scale), _dt(a), _stream())
     return out
 
 
 def conv3x3(x, w, out, NB, H, W, Cin, Cout, bias=None, residual=None, rowbias=None, stride2=False, out_scale=1.0):
     """x: NHWC [NB,H,W,Cin] (or phase-split [NB,4,H,W,Cin] when stride2; H,W = output dims); w: [Cout, 9*Cin];
     out: [NB*H*W, >=Cout] rows."""
-    call("cid_conv3x3", _p(x), _p(w), _p(out), out.stride(0), NB, H, W, Cin, Cout, 1 if stride2 else 0, _p(bias), _p(residual),
-         0 if residual is None else residual.stride(0), _p(rowbias), 0 if rowbias is None else rowbias.stride(0),
-         float(out_scale), _dt(x), _stream())
+    M = NB * H * W
+    with _prof("conv3x3", 2.0 * M * Cout * 9 * Cin, 2.0 * (M * Cin * (4 if stride2 else 1) + 9 * Cin * Cout + M * Cout)):
+        call("cid_conv3x3", _p(x), _p(w), _p(out), out.stride(0), NB, H, W, Cin, Cout, 1 if stride2 else 0, _p(bias), _p(residual),
+             0 if residual is None else residual.stride(0), _p(rowbias), 0 if rowbias is None else rowbias.stride(0),
+             float(out_scale), _dt(x), _stream())
     return out
 
 
 def attn_self(q, k, vt, out, B, H, N, d):
     """q,k: views [B*N, >=H*d] (row pitch = stride(0)); vt: [B*H, d, N]; out: [B*N, H*d]."""
-    call("cid_attn_self", _p(q), q.stride(0), _p(k), k.stride(0), _p(vt), _p(out), out.stride(0), B, H, N, d, _dt(q), _stream())
+    with _prof("attn_self", 4.0 * B * H * N * N * d, 2.0 * 4 * B * N * H * d):
+        call("cid_attn_self", _p(q), q.stride(0), _p(k), k.stride(0), _p(vt), _p(out), out.stride(0), B, H, N, d, _dt(q), _stream())
     return out
 
 
 def attn_cross(q, k_cat, vt_cat, out, B, H, N, d, n_text, n_ip, ip_scale):
-    call("cid_attn_cross", _p(q), q.stride(0), _p(k_cat), _p(vt_cat), _p(out), out.stride(0), B, H, N, d, n_text, n_ip,
-         float(ip_scale), _dt(q), _stream())
+    with _prof("attn_cross", 4.0 * B * H * N * (n_text + n_ip) * d, 2.0 * 2 * B * N * H * d):
+        call("cid_attn_cross", _p(q), q.stride(0), _p(k_cat), _p(vt_cat), _p(out), out.stride(0), B, H, N, d, n_text, n_ip,
+             float(ip_scale), _dt(q), _stream())
     return out
 
 

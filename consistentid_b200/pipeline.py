@@ -74,7 +74,7 @@ class B200Denoiser:
     @torch.no_grad()
     def __call__(self, latents, null_embeds, augmented_embeds, text_embeds, num_inference_steps=30, guidance_scale=5.0,
                  start_merge_step=0, neg_pooled=None, pooled_text_only=None, pooled_facial=None, add_time_ids=None,
-                 null_embeds_facial=None, output_device=None):
+                 null_embeds_facial=None, output_device=None, profile=False):
         """latents [B,4,h,w] already multiplied by ``scheduler.init_noise_sigma`` (host or device, any float dtype).
         SD1.5: (null, augmented, text_only) each [1,81,cad] (chunk(3) of prompt_embeds, :527-531).
         SDXL: additionally pooled embeds [1,1280] x3 and add_time_ids [1,6]; ``null_embeds_facial`` is the uncond prompt of
@@ -117,9 +117,13 @@ class B200Denoiser:
         st["step"].zero_()
         u._buf("t_dev", (1,), torch.float32).copy_(ts[:1])
         ops.latents_to_input(st["x"], u._buf("x_in", (NB * HW, CIN_PAD)), CIN_PAD, B, HW, coef)
+        if profile:                       # bench.py roofline pass: event-bracket every tensor-core launch of the step loop only
+            ops.profile_begin()
         for i in range(n):
             phase = "text" if i <= start_merge_step else "aug"
             self._step(phase, phases[phase], st)
+        if profile:
+            self.last_profile = ops.profile_end()
         out = st["x16"].reshape(B, 4, h, w)
         if output_device is not None:
             return out.to(output_device)
