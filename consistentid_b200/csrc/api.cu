@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 
 #include <cudaTypedefs.h>
@@ -12,6 +13,7 @@
 #include "attn_tc.cuh"
 #include "elementwise.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 
 using namespace cid;
 
@@ -87,7 +89,51 @@ int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap&
   CID_CHECK_LAUNCH("gemm_tc_kernel");
   return 0;
 }
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) g_num_sms = n;
+    else g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+// 1 = one-tile-per-CTA kernel (gemm_tc.cuh), 2 = persistent kernel with double-buffered TMEM (gemm_tc2.cuh, default)
+int g_gemm_version = 0;
+int gemm_version() {
+  if (g_gemm_version == 0) {
+    const char* e = getenv("CID_GEMM_VERSION");
+    g_gemm_version = (e && e[0] == '1') ? 1 : 2;
+  }
+  return g_gemm_version;
+}
+
+template <int BN, int STAGES>
+int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
+  using SM = Gemm2Smem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    int rc = set_smem(gemm_tc2_kernel<BN, STAGES>, SM::TOTAL, "gemm_tc2_kernel");
+    if (rc) return rc;
+    configured = true;
+  }
+  const int n_tiles = (g.N + BN - 1) / BN;
+  const int total = n_tiles * m_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_tc2_kernel<BN, STAGES><<<grid, GEMM2_THREADS, SM::TOTAL, st>>>(a1, a2, b, g, n_tiles, total);
+  CID_CHECK_LAUNCH("gemm_tc2_kernel");
+  return 0;
+}
+
 int dispatch_gemm(int bn, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
+  if (gemm_version() == 2) {
+    switch (bn) {
+      case 160: return launch_gemm2<160, 5>(a1, a2, b, g, m_tiles, st);
+      case 64: return launch_gemm2<64, 8>(a1, a2, b, g, m_tiles, st);
+      case 16: return launch_gemm2<16, 8>(a1, a2, b, g, m_tiles, st);
+    }
+    return fail(CID_ERR_UNSUPPORTED, "no GEMM instantiation for tile N %d", bn);
+  }
   switch (bn) {
     case 160: return launch_gemm<160, 3>(a1, a2, b, g, m_tiles, st);
     case 64: return launch_gemm<64, 4>(a1, a2, b, g, m_tiles, st);

@@ -1,0 +1,304 @@
+// Persistent tcgen05 GEMM / implicit-GEMM conv3x3 (v2 of gemm_tc.cuh; same arguments, same math).
+//
+// One CTA per SM loops over output tiles (tile = blockIdx.x + i*gridDim.x, N-tile fastest so CTAs running at the same
+// time share the activation (A) tile in L2).  Roles (320 threads):
+//   warp 0      TMA producer - keeps the STAGES-deep smem ring full ACROSS tile boundaries
+//   warp 1      TMEM allocator (512 columns = two accumulators) + tcgen05.mma issuer; alternates accumulators so the
+//               main loop of tile i+1 overlaps the epilogue of tile i
+//   warps 2-9   epilogue: two warps per TMEM lane quarter, each draining half of the tile's columns in 16-column
+//               tcgen05.ld chunks; residual rows are prefetched into registers BEFORE waiting for the accumulator and the
+//               bias slice of the tile is staged once in smem, so no global-load latency sits between TMEM and the stores
+#pragma once
+#include "elementwise.cuh"
+#include "gemm_tc.cuh"
+
+namespace cid {
+
+constexpr int GEMM2_THREADS = 320;
+constexpr int GEMM2_EPI_THREADS = 256;
+
+template <int BN, int STAGES>
+struct Gemm2Smem {
+  static constexpr int A_BYTES = GEMM_BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BIAS_OFF = BAR_OFF + 256;             // 2 x BN floats
+  static constexpr int TOTAL = BIAS_OFF + 2 * BN * 4 + 1024;
+};
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM2_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmB, const GemmArgs g, const int n_tiles, const int total_tiles) {
+  static_assert(BN % 32 == 0 || BN == 16, "column split");
+  constexpr int ACC_STRIDE = 256;                              // TMEM column offset between the two accumulators
+  using SM = Gemm2Smem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + SM::BAR_OFF;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto acc_full = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto acc_empty = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + SM::BAR_OFF + 8 * (2 * STAGES + 4));
+  float* bias_s = reinterpret_cast<float*>(smem_gen + SM::BIAS_OFF);
+
+  const int warp = warp_id();
+  const int lane = lane_id();
+  const int kb_per_tap = g.kblocks_a1 + g.kblocks_a2;
+  const int num_kb = g.taps * kb_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA1);
+    if (g.kblocks_a2 > 0) tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), GEMM2_EPI_THREADS); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_origin = [&](int mt, int& tn0, int& ty0, int& tx0) {
+    const int tx = mt % g.tiles_x;
+    const int rest = mt / g.tiles_x;
+    tx0 = tx * g.TW; ty0 = (rest % g.tiles_y) * g.TH; tn0 = (rest / g.tiles_y) * g.TN;
+  };
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      const uint32_t a_bytes = (g.a_mode == A_GEMM) ? uint32_t(SM::A_BYTES) : uint32_t(g.TW * g.TH * g.TN * 128);
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % n_tiles, mt = tile / n_tiles;
+        int tn0 = 0, ty0 = 0, tx0 = 0;
+        if (g.a_mode != A_GEMM) tile_origin(mt, tn0, ty0, tx0);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * SM::STAGE_BYTES;
+          const uint32_t sb = sa + SM::A_BYTES;
+          mbar_expect_tx(full_bar(stage), a_bytes + uint32_t(SM::B_BYTES));
+          const int tap = kb / kb_per_tap;
+          const int cb = kb - tap * kb_per_tap;
+          if (g.a_mode == A_GEMM) {
+            if (cb < g.kblocks_a1) tma_load_2d(sa, &tmA1, full_bar(stage), cb * GEMM_BK, mt * GEMM_BM);
+            else tma_load_2d(sa, &tmA2, full_bar(stage), (cb - g.kblocks_a1) * GEMM_BK, mt * GEMM_BM);
+          } else if (g.a_mode == A_CONV) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            tma_load_4d(sa, &tmA1, full_bar(stage), cb * GEMM_BK, tx0 + kx - 1, ty0 + ky - 1, tn0);
+          } else {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const int py = (ky == 1) ? 0 : 1, dy = (ky == 0) ? -1 : 0;
+            const int px = (kx == 1) ? 0 : 1, dx = (kx == 0) ? -1 : 0;
+            tma_load_5d(sa, &tmA1, full_bar(stage), cb * GEMM_BK, tx0 + dx, ty0 + dy, py * 2 + px, tn0);
+          }
+          tma_load_2d(sb, &tmB, full_bar(stage), kb * GEMM_BK, nt * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    const uint32_t idesc = make_idesc(GEMM_BM, BN, g.is_bf16);
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int ab = it & 1;
+      const uint32_t aphase = uint32_t(it >> 1) & 1u;
+      mbar_wait(acc_empty(ab), aphase ^ 1u);              // epilogue has drained this accumulator (first use: free)
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + ab * ACC_STRIDE;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_base + stage * SM::STAGE_BYTES;
+          const uint32_t sb = sa + SM::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            umma_ss(tmem_acc, make_desc_sw128(sa + k * 32), make_desc_sw128(sb + k * 32), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (kb == num_kb - 1) umma_commit(acc_full(ab));
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ================================================================ epilogue (warps 2..9)
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;                              // which half of the tile's columns this warp drains
+    const int r = quarter * 32 + lane;
+    const int et = threadIdx.x - 64;                       // 0..255
+    const int bf = g.is_bf16;
+    const bool geglu = g.epi == EPI_GEGLU;
+    // column range [c_beg, c_end) in 16-column chunks (GEGLU: over the value half only)
+    constexpr int NCHUNK = BN / 16;
+    constexpr int NCHUNK_G = (BN / 2) / 16 > 0 ? (BN / 2) / 16 : 1;
+    const int nch = geglu ? NCHUNK_G : NCHUNK;
+    const int ch_beg = half == 0 ? 0 : (nch + 1) / 2;
+    const int ch_end = half == 0 ? (nch + 1) / 2 : nch;
+    constexpr int MAXCH = (NCHUNK + 1) / 2;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int ab = it & 1;
+      const uint32_t aphase = uint32_t(it >> 1) & 1u;
+      const int nt = tile % n_tiles, mt = tile / n_tiles;
+      const int n0 = nt * BN;
+      long long grow; bool row_ok;
+      if (g.a_mode == A_GEMM) {
+        grow = (long long)mt * GEMM_BM + r;
+        row_ok = grow < g.M;
+      } else {
+        int tn0, ty0, tx0;
+        tile_origin(mt, tn0, ty0, tx0);
+        const int per_img = g.TW * g.TH;
+        const int dn = r / per_img, rem = r - dn * per_img;
+        const int dy = rem / g.TW, dx = rem - dy * g.TW;
+        const int n = tn0 + dn, y = ty0 + dy, x = tx0 + dx;
+        row_ok = (dn < g.TN) && (n < g.NB) && (y < g.H) && (x < g.W);
+        grow = ((long long)n * g.H + y) * g.W + x;
+      }
+      // stage this tile's bias slice (fp32) in smem; buffer alternates with the accumulator
+      float* bs = bias_s + ab * BN;
+      for (int j = et; j < BN; j += GEMM2_EPI_THREADS) bs[j] = (g.bias && n0 + j < g.N) ? load16(g.bias, n0 + j, bf) : 0.f;
+      // prefetch residual rows for this thread's chunks (latency overlaps the wait for the accumulator)
+      uint4 res[MAXCH][2];
+      const bool use_res = g.residual != nullptr && !geglu && row_ok;
+      const uint16_t* rrow = use_res ? reinterpret_cast<const uint16_t*>(g.residual) + grow * g.ldr + n0 : nullptr;
+      const bool res_vec = use_res && ((reinterpret_cast<uintptr_t>(rrow) & 15) == 0) && (n0 + BN <= g.N);
+#pragma unroll
+      for (int c = 0; c < MAXCH; ++c) {
+        const int ch = ch_beg + c;
+        if (res_vec && ch < ch_end) {
+          res[c][0] = reinterpret_cast<const uint4*>(rrow + ch * 16)[0];
+          res[c][1] = reinterpret_cast<const uint4*>(rrow + ch * 16)[1];
+        }
+      }
+      epi_bar_sync();                                       // bias slice visible to all epilogue threads
+      mbar_wait(acc_full(ab), aphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ab * ACC_STRIDE + (uint32_t(quarter * 32) << 16);
+
+      if (BN >= 32 && geglu) {
+        constexpr int HALF = BN / 2;
+        const int out_col0 = nt * HALF;
+#pragma unroll
+        for (int c = 0; c < MAXCH; ++c) {
+          const int ch = ch_beg + c;
+          if (ch < ch_end) {
+            uint32_t a[16], b[16];
+            tmem_ld_x16(t_row + ch * 16, a);
+            tmem_ld_x16(t_row + HALF + ch * 16, b);
+            tmem_ld_wait();
+            if (row_ok) {
+              uint32_t packed[8];
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const float v0 = __uint_as_float(a[j]) + bs[ch * 16 + j], v1 = __uint_as_float(a[j + 1]) + bs[ch * 16 + j + 1];
+                const float g0 = __uint_as_float(b[j]) + bs[HALF + ch * 16 + j], g1 = __uint_as_float(b[j + 1]) + bs[HALF + ch * 16 + j + 1];
+                const float2 vr = unpack16(pack16(v0, v1, bf), bf), gr = unpack16(pack16(g0, g1, bf), bf);
+                packed[j >> 1] = pack16(vr.x * gelu_erf(gr.x), vr.y * gelu_erf(gr.y), bf);
+              }
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(g.C) + grow * g.ldc + out_col0 + ch * 16);
+              dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+              dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < MAXCH; ++c) {
+          const int ch = ch_beg + c;
+          if (ch < ch_end) {
+            uint32_t a[16];
+            tmem_ld_x16(t_row + ch * 16, a);
+            tmem_ld_wait();
+            const int col0 = n0 + ch * 16;
+            if (row_ok && col0 < g.N) {
+              const bool full = (col0 + 16 <= g.N);
+              float v[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(a[j]) + bs[ch * 16 + j];
+              if (g.rowbias) {
+                const uint16_t* rb = reinterpret_cast<const uint16_t*>(g.rowbias) + (grow / g.rows_per_group) * g.ld_rowbias + col0;
+                if (full && ((reinterpret_cast<uintptr_t>(rb) & 15) == 0)) {
+                  float f0[8], f1[8];
+                  unpack8(reinterpret_cast<const uint4*>(rb)[0], f0, bf); unpack8(reinterpret_cast<const uint4*>(rb)[1], f1, bf);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) { v[j] += f0[j]; v[8 + j] += f1[j]; }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) if (full || col0 + j < g.N) v[j] += load16(rb, j, bf);
+                }
+              }
+              if (g.epi == EPI_QKV && col0 >= g.n_split) {
+                const int b = int(grow / g.ntok), tok = int(grow - (long long)b * g.ntok);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int vc = col0 + j - g.n_split;
+                  if (full || col0 + j < g.N) {
+                    const int h = vc / g.hdim, dd = vc - h * g.hdim;
+                    store16(g.Vt, ((size_t)(b * g.heads + h) * g.hdim + dd) * g.ntok + tok, v[j], bf);
+                  }
+                }
+              } else {
+                if (use_res) {
+                  if (res_vec) {
+                    float f0[8], f1[8];
+                    unpack8(res[c][0], f0, bf); unpack8(res[c][1], f1, bf);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { v[j] += f0[j]; v[8 + j] += f1[j]; }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (full || col0 + j < g.N) v[j] += load16(rrow, ch * 16 + j, bf);
+                  }
+                }
+                if (g.out_scale != 1.0f) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] *= g.out_scale;
+                }
+                uint16_t* crow = reinterpret_cast<uint16_t*>(g.C) + grow * g.ldc + col0;
+                if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+                  float lo[8], hi[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+                  reinterpret_cast<uint4*>(crow)[0] = pack8(lo, bf);
+                  reinterpret_cast<uint4*>(crow)[1] = pack8(hi, bf);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) if (full || col0 + j < g.N) store16(crow, j, v[j], bf);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty(ab));                           // this thread no longer reads accumulator `ab`
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace cid

@@ -67,7 +67,7 @@ class EulerRef(_Base):
     def set_timesteps(self, n, device=None):
         self.num_inference_steps = n
         ts = self._leading(n).astype(np.float32)
-        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
         sig = np.interp(ts, np.arange(0, len(sig)), sig)
         self.sigmas = torch.from_numpy(np.concatenate([sig, [0.0]]).astype(np.float32)).to(device)
         self.timesteps = torch.from_numpy(ts).to(device)
