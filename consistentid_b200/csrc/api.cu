@@ -128,6 +128,7 @@ int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap
 int dispatch_gemm(int bn, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
   if (gemm_version() == 2) {
     switch (bn) {
+      case 256: return launch_gemm2<256, 4>(a1, a2, b, g, m_tiles, st);
       case 160: return launch_gemm2<160, 5>(a1, a2, b, g, m_tiles, st);
       case 64: return launch_gemm2<64, 8>(a1, a2, b, g, m_tiles, st);
       case 16: return launch_gemm2<16, 8>(a1, a2, b, g, m_tiles, st);
@@ -196,6 +197,10 @@ int cid_version(void) { return 100; }
 const char* cid_last_error(void) { return g_err; }
 
 int cid_gemm_tile_n(int N, int epi) {
+  // 256-wide tiles cut the L2->SMEM bytes per FLOP (the limiter of the 128x160 tile) wherever the width allows
+  static int allow256 = -1;
+  if (allow256 < 0) { const char* e = getenv("CID_GEMM_NO256"); allow256 = (e && e[0] == '1') ? 0 : 1; }
+  if (allow256 && gemm_version() == 2 && N % 256 == 0 && N >= 1024) return 256;
   if (epi == CID_EPI_GEGLU) {
     if (N % 160 == 0) return 160;
     if (N % 64 == 0) return 64;

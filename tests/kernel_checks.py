@@ -321,6 +321,8 @@ CHECKS = {
     "conv_nonsq": (check_conv, dict(NB=2, H=24, W=16, Cin=64, Cout=160)),
     "conv_w96": (check_conv, dict(NB=1, H=64, W=96, Cin=64, Cout=160)),
     "conv_out4": (check_conv, dict(NB=2, H=32, W=32, Cin=320, Cout=4)),
+    "conv_1280": (check_conv, dict(NB=2, H=16, W=16, Cin=256, Cout=1280, rowbias=True, residual=True)),
+    "gemm_n3840_qkv": (check_gemm_qkv, dict(B=1, ntok=256, C=1280, heads=20, dtype=B16)),
     "conv_s2": (check_conv, dict(NB=2, H=16, W=16, Cin=128, Cout=160, stride2=True)),
     "conv_s2_64": (check_conv, dict(NB=1, H=32, W=32, Cin=64, Cout=320, stride2=True, dtype=B16)),
     "attn_self_d64": (check_attn_self, dict(B=2, H=2, N=256, d=64)),
