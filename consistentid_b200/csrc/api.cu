@@ -11,6 +11,7 @@
 
 #include "../../include/cidb200.h"
 #include "attn_tc.cuh"
+#include "attn_tc2.cuh"
 #include "elementwise.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
@@ -164,6 +165,21 @@ int launch_attn_self(const CUtensorMap& q, const CUtensorMap& k, const CUtensorM
   CID_CHECK_LAUNCH("attn_self_kernel");
   return 0;
 }
+int g_attn_version = 0;
+int attn_version() {
+  if (g_attn_version == 0) { const char* e = getenv("CID_ATTN_VERSION"); g_attn_version = (e && e[0] == '1') ? 1 : 2; }
+  return g_attn_version;
+}
+template <int D_PAD>
+int launch_attn_self2(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
+  using C = Attn2Cfg<D_PAD>;
+  static bool configured = false;
+  if (!configured) { int rc = set_smem(attn_self2_kernel<D_PAD>, C::TOTAL, "attn_self2_kernel"); if (rc) return rc; configured = true; }
+  dim3 grid((a.Nq + 127) / 128, a.H, a.B);
+  attn_self2_kernel<D_PAD><<<grid, ATTN_THREADS, C::TOTAL, st>>>(q, k, v, a);
+  CID_CHECK_LAUNCH("attn_self2_kernel");
+  return 0;
+}
 template <int D_PAD>
 int launch_attn_cross(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
   using C = CrossCfg<D_PAD>;
@@ -289,6 +305,16 @@ int cid_attn_self(const void* Q, long long q_pitch, const void* K, long long k_p
   AttnArgs a{}; a.B = B; a.H = H; a.Nq = N; a.Nkv = N; a.d = d; a.scale_log2 = 1.4426950408889634f / sqrtf(float(d));
   a.O = O; a.ldo = ldo; a.is_bf16 = dtype == CID_BF16;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (attn_version() == 2) {
+    switch (dp) {
+      case 32: return launch_attn_self2<32>(tq, tk, tv, a, st);
+      case 48: return launch_attn_self2<48>(tq, tk, tv, a, st);
+      case 64: return launch_attn_self2<64>(tq, tk, tv, a, st);
+      case 80: return launch_attn_self2<80>(tq, tk, tv, a, st);
+      case 128: return launch_attn_self2<128>(tq, tk, tv, a, st);
+      case 160: return launch_attn_self2<160>(tq, tk, tv, a, st);
+    }
+  }
   switch (dp) {
     case 32: return launch_attn_self<32>(tq, tk, tv, a, st);
     case 48: return launch_attn_self<48>(tq, tk, tv, a, st);
@@ -356,7 +382,10 @@ int cid_gn_apply(const void* x1, int C1, const void* x2, int C2, int NB, int HW,
   const int C = C1 + C2;
   if (!x1 || !sums || !gamma || !beta || !y || C1 % 8 || C2 % 8 || C % groups) return fail(CID_ERR_ARG, "cid_gn_apply: bad arguments");
   const long long total = (long long)NB * HW * (C / 8);
-  gn_apply_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  if (C > 4096) return fail(CID_ERR_UNSUPPORTED, "cid_gn_apply: C=%d > 4096", C);
+  int slabs = grid_for((long long)HW * (C / 8), 256) / NB;
+  if (slabs < 1) slabs = 1;
+  gn_apply_kernel<<<dim3(slabs, NB), 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       (const uint16_t*)x1, C1, (const uint16_t*)x2, C2, HW, groups, sums, (const uint16_t*)gamma, (const uint16_t*)beta, eps, silu,
       (uint16_t*)y, total, dtype == CID_BF16);
   CID_CHECK_LAUNCH("gn_apply_kernel");

@@ -1,0 +1,301 @@
+// attn_self2_kernel - v2 of the flash self-attention (same operands / results as attn_self_kernel in attn_tc.cuh).
+// ncu on v1 showed the kernel is instruction-issue bound in the softmax warps (72 % issue-active, tensor pipe 16 %), so v2
+// removes instructions per score element:
+//   * full key tiles take an unmasked path (no per-element ISETP / predication);
+//   * probabilities are produced by the packed special-function path: (s - m) * c in fp32 -> cvt.rn.{f16x2|bf16x2}
+//     -> ex2.approx.{f16x2|bf16x2}; the packed result IS the P operand (no F2FP, half the MUFU issues);
+//   * the row sum is not accumulated by the softmax threads at all: an extra N=16 tcgen05.mma multiplies P by a 128-byte
+//     all-ones tile (non-swizzled descriptor with LBO = SBO = 0, every core matrix aliases the same 128 bytes), so
+//     l_tile = P . 1 lands in TMEM next to P . V, summed in fp32 from exactly the rounded P the value MMA uses;
+//   * row max uses 3-input max.
+#pragma once
+#include "attn_tc.cuh"
+
+namespace cid {
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// p = 2^x for two fp32 inputs, packed 16-bit result (low half = x0)
+template <int BF>
+__device__ __forceinline__ uint32_t ex2_pack(float x0, float x1) {
+  uint32_t h, p;
+  if (BF) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+    asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(p) : "r"(h));
+  } else {
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(p) : "r"(h));
+  }
+  return p;
+}
+// K-major, NO swizzle, LBO = SBO = 0: all 8x16-byte core matrices alias the 128 bytes at `saddr`
+__device__ __forceinline__ uint64_t make_desc_alias128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= uint64_t((saddr & 0x3FFFF) >> 4);
+  d |= uint64_t(1) << 46;                        // descriptor version; layout type 0 = SWIZZLE_NONE
+  return d;
+}
+
+// one 32-column chunk of scores -> 16 packed probabilities
+template <int BF>
+__device__ __forceinline__ void exp_chunk(const uint32_t (&v)[32], float c, float nmc, uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 2)
+    pk[i >> 1] = ex2_pack<BF>(fmaf(__uint_as_float(v[i]), c, nmc), fmaf(__uint_as_float(v[i + 1]), c, nmc));
+}
+template <int BF>
+__device__ __forceinline__ void exp_chunk_masked(const uint32_t (&v)[32], float c, float nmc, int nvalid, uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const float x0 = (i < nvalid) ? fmaf(__uint_as_float(v[i]), c, nmc) : -INFINITY;
+    const float x1 = (i + 1 < nvalid) ? fmaf(__uint_as_float(v[i + 1]), c, nmc) : -INFINITY;
+    pk[i >> 1] = ex2_pack<BF>(x0, x1);
+  }
+}
+
+template <int D_PAD>
+struct Attn2Cfg : AttnCfg<D_PAD> {
+  static constexpr int TMEM_COLS = (128 + D_PAD + 16 <= 256) ? 256 : 512;
+  static constexpr int MIN_CTAS = (AttnCfg<D_PAD>::TOTAL <= 115000 && TMEM_COLS == 256) ? 2 : 1;
+  static constexpr int OFF_ONES = AttnCfg<D_PAD>::OFF_BAR + 128;      // 128-byte all-ones tile inside the barrier block
+};
+
+template <int D_PAD>
+__global__ void __launch_bounds__(ATTN_THREADS, Attn2Cfg<D_PAD>::MIN_CTAS)
+attn_self2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmVt, const AttnArgs a) {
+  using C = Attn2Cfg<D_PAD>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if ((sbase & 1023u) != 0) { if (threadIdx.x == 0) printf("cid: attn smem base not 1024-aligned\n"); __trap(); }
+  const uint32_t bar0 = sbase + C::OFF_BAR;
+  const uint32_t q_full = bar0;
+  auto k_full = [&](int s) { return bar0 + 8u * (1 + s); };
+  auto k_empty = [&](int s) { return bar0 + 8u * (1 + STAGES + s); };
+  auto v_full = [&](int s) { return bar0 + 8u * (1 + 2 * STAGES + s); };
+  auto v_empty = [&](int s) { return bar0 + 8u * (1 + 3 * STAGES + s); };
+  const uint32_t s_full = bar0 + 8u * (1 + 4 * STAGES);
+  const uint32_t s_free = s_full + 8u;
+  const uint32_t p_full = s_full + 16u;
+  const uint32_t pv_full = s_full + 24u;
+  const uint32_t pv_free = s_full + 32u;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + C::OFF_BAR + 8 * (6 + 4 * STAGES));
+  static_assert(8 * (6 + 4 * STAGES) + 4 <= 128, "barrier block overflows into the ones tile");
+
+  const int warp = warp_id(), lane = lane_id();
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int T = (a.Nkv + 127) / 128;
+  const int bf = a.is_bf16;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmVt); }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int s = 0; s < STAGES; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
+      mbar_init(s_full, 1); mbar_init(s_free, 128); mbar_init(p_full, 128); mbar_init(pv_full, 1); mbar_init(pv_free, 128);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<C::TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  }
+  if (warp == 2) {                                              // 128-byte all-ones tile (1.0 in fp16 / bf16)
+    reinterpret_cast<uint32_t*>(smem_raw + C::OFF_ONES)[lane] = bf ? 0x3F803F80u : 0x3C003C00u;
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_S = tmem, tmem_PV = tmem + 128, tmem_L = tmem + 128 + D_PAD;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, C::Q_BYTES);
+      for (int ch = 0; ch < C::NCH; ++ch) tma_load_4d(sbase + ch * 16384, &tmQ, q_full, ch * 64, q0, h, b);
+      int stage = 0; uint32_t phase = 0;
+      for (int j = 0; j < T; ++j) {
+        const int k0 = j * 128;
+        mbar_wait(k_empty(stage), phase ^ 1u);
+        mbar_expect_tx(k_full(stage), C::K_BYTES);
+        for (int ch = 0; ch < C::NCH; ++ch)
+          tma_load_4d(sbase + C::OFF_K + stage * C::K_BYTES + ch * 16384, &tmK, k_full(stage), ch * 64, k0, h, b);
+        mbar_wait(v_empty(stage), phase ^ 1u);
+        mbar_expect_tx(v_full(stage), C::V_BYTES);
+        for (int kc = 0; kc < 2; ++kc)
+          tma_load_3d(sbase + C::OFF_V + stage * C::V_BYTES + kc * C::V_CHUNK, &tmVt, v_full(stage), k0 + kc * 64, 0, b * a.H + h);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    const uint32_t idesc_s = make_idesc(128, 128, bf);
+    const uint32_t idesc_pv = make_idesc(128, D_PAD, bf);
+    const uint32_t idesc_l = make_idesc(128, 16, bf);
+    const uint64_t ones_desc = make_desc_alias128(sbase + C::OFF_ONES);
+    auto issue_S = [&](int stage) {
+      const uint32_t sk = sbase + C::OFF_K + stage * C::K_BYTES;
+#pragma unroll
+      for (int ch = 0; ch < C::NCH; ++ch) {
+        const int ksteps = (D_PAD - ch * 64 >= 64) ? 4 : (D_PAD - ch * 64) / 16;
+#pragma unroll
+        for (int kk = 0; kk < ksteps; ++kk)
+          umma_ss(tmem_S, make_desc_sw128(sbase + ch * 16384 + kk * 32), make_desc_sw128(sk + ch * 16384 + kk * 32),
+                  idesc_s, (ch | kk) ? 1u : 0u);
+      }
+    };
+    mbar_wait(q_full, 0);
+    int stage = 0; uint32_t phase = 0;
+    int nstage = 0; uint32_t nphase = 0;
+    mbar_wait(k_full(0), 0);
+    tc_fence_after();
+    if (lane == 0) { issue_S(0); umma_commit(s_full); umma_commit(k_empty(0)); }
+    __syncwarp();
+    if (++nstage == STAGES) { nstage = 0; nphase ^= 1u; }
+    for (int j = 0; j < T; ++j) {
+      if (j + 1 < T) {
+        mbar_wait(k_full(nstage), nphase);
+        mbar_wait(s_free, uint32_t(j & 1));
+        tc_fence_after();
+        if (lane == 0) { issue_S(nstage); umma_commit(s_full); umma_commit(k_empty(nstage)); }
+        __syncwarp();
+        if (++nstage == STAGES) { nstage = 0; nphase ^= 1u; }
+      }
+      mbar_wait(p_full, uint32_t(j & 1));
+      mbar_wait(v_full(stage), phase);
+      if (j > 0) mbar_wait(pv_free, uint32_t((j - 1) & 1));
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sv = sbase + C::OFF_V + stage * C::V_BYTES;
+        const uint32_t sp = sbase + C::OFF_P;
+#pragma unroll
+        for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t pdesc = make_desc_sw128(sp + kc * 16384 + kk * 32);
+            umma_ss(tmem_PV, pdesc, make_desc_sw128(sv + kc * C::V_CHUNK + kk * 32), idesc_pv, (kc | kk) ? 1u : 0u);
+            umma_ss(tmem_L, pdesc, ones_desc, idesc_l, (kc | kk) ? 1u : 0u);      // row sums of P
+          }
+        umma_commit(pv_full);
+        umma_commit(v_empty(stage));
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    }
+  } else {
+    // ============================================================ softmax + output (warps 2..5, one query row per thread)
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = uint32_t(quarter * 32) << 16;
+    uint8_t* sP = smem_raw + C::OFF_P;
+    float o[D_PAD];
+#pragma unroll
+    for (int i = 0; i < D_PAD; ++i) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f, alpha_pending = 0.f;
+    const float c = a.scale_log2;
+
+    auto accumulate_pv = [&](float alpha) {
+      {
+        uint32_t v[16];
+        tmem_ld_x16(tmem_L + lane_off, v);
+        tmem_ld_wait();
+        l = l * alpha + __uint_as_float(v[0]);
+      }
+#pragma unroll
+      for (int cc = 0; cc < D_PAD; cc += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(tmem_PV + lane_off + cc, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[cc + i] = fmaf(o[cc + i], alpha, __uint_as_float(v[i]));
+      }
+    };
+
+    for (int j = 0; j < T; ++j) {
+      const int kvalid = a.Nkv - j * 128;
+      const bool full_tile = kvalid >= 128;
+      mbar_wait(s_full, uint32_t(j & 1));
+      tc_fence_after();
+      // ---- pass 1: row max
+      float mx = -INFINITY;
+      if (full_tile) {
+#pragma unroll 1
+        for (int cc = 0; cc < 128; cc += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(tmem_S + lane_off + cc, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+        }
+      } else {
+#pragma unroll 1
+        for (int cc = 0; cc < 128; cc += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(tmem_S + lane_off + cc, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (cc + i < kvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = fast_exp2((m - m_new) * c);
+      const float nmc = -m_new * c;
+      if (j > 0) {
+        mbar_wait(pv_full, uint32_t((j - 1) & 1));
+        tc_fence_after();
+        accumulate_pv(alpha_pending);
+        tc_fence_before();
+        mbar_arrive(pv_free);
+      }
+      alpha_pending = alpha;
+      m = m_new;
+      // ---- pass 2: P = 2^((s - m) c), packed, straight into the swizzled A-operand tile
+#pragma unroll 1
+      for (int cc = 0; cc < 128; cc += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_S + lane_off + cc, v);
+        tmem_ld_wait();
+        if (cc == 96) { tc_fence_before(); mbar_arrive(s_free); }
+        uint32_t pk[16];
+        if (full_tile) {
+          if (bf) exp_chunk<1>(v, c, nmc, pk); else exp_chunk<0>(v, c, nmc, pk);
+        } else {
+          if (bf) exp_chunk_masked<1>(v, c, nmc, kvalid - cc, pk); else exp_chunk_masked<0>(v, c, nmc, kvalid - cc, pk);
+        }
+        uint8_t* tile = sP + (cc >> 6) * 16384;
+        const int col = cc & 63;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          st_sw128(tile, r, col + q * 8, make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]));
+      }
+      fence_proxy_async();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(pv_full, uint32_t((T - 1) & 1));
+    tc_fence_after();
+    accumulate_pv(alpha_pending);
+    tc_fence_before();
+    const float inv = 1.f / l;
+    if (q0 + r < a.Nq) {
+      uint16_t* dst = reinterpret_cast<uint16_t*>(a.O) + ((long long)b * a.Nq + q0 + r) * a.ldo + h * a.d;
+#pragma unroll
+      for (int i = 0; i < D_PAD; i += 8) {
+        if (i < a.d) {
+          uint4 u;
+          u.x = pack16(o[i] * inv, o[i + 1] * inv, bf); u.y = pack16(o[i + 2] * inv, o[i + 3] * inv, bf);
+          u.z = pack16(o[i + 4] * inv, o[i + 5] * inv, bf); u.w = pack16(o[i + 6] * inv, o[i + 7] * inv, bf);
+          *reinterpret_cast<uint4*>(dst + i) = u;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<C::TMEM_COLS>(tmem); }
+}
+
+}  // namespace cid

@@ -68,30 +68,45 @@ __global__ void __launch_bounds__(256)
 gn_apply_kernel(const uint16_t* __restrict__ x1, int C1, const uint16_t* __restrict__ x2, int C2, int HW, int groups,
                 const float* __restrict__ sums, const uint16_t* __restrict__ gamma, const uint16_t* __restrict__ beta,
                 float eps, int do_silu, uint16_t* __restrict__ y, long long total_vec, int bf) {
+  // grid (slabs, NB): a block serves ONE sample, so the per-channel affine (scale = rstd*gamma, shift = beta - mean*scale)
+  // is built once in smem and the streaming loop is one FMA (+ SiLU) per element.
+  extern __shared__ float aff[];                 // [2 * C]
   const int C = C1 + C2, V = C / 8, cpg = C / groups;
+  const int n = blockIdx.y;
   const float inv_n = 1.f / (float(HW) * float(cpg));
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float sm = sums[((size_t)n * groups + g) * 2], sq = sums[((size_t)n * groups + g) * 2 + 1];
+    const float mean = sm * inv_n;
+    const float rstd = rsqrtf(fmaxf(sq * inv_n - mean * mean, 0.f) + eps);
+    const float sc = rstd * load16(gamma, c, bf);
+    aff[c] = sc;
+    aff[C + c] = load16(beta, c, bf) - mean * sc;
+  }
+  __syncthreads();
+  const long long per_sample = (long long)HW * V;
+  const uint16_t* x1n = x1 + (size_t)n * HW * C1;
+  const uint16_t* x2n = x2 ? x2 + (size_t)n * HW * C2 : nullptr;
+  uint16_t* yn = y + (size_t)n * HW * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample; i += (long long)gridDim.x * blockDim.x) {
     const int vec = int(i % V);
-    const long long pix = i / V;                 // n * HW + p
-    const int n = int(pix / HW);
+    const long long pix = i / V;
     const int c0 = vec * 8;
-    const uint4 u = (c0 < C1) ? *reinterpret_cast<const uint4*>(x1 + pix * C1 + c0)
-                              : *reinterpret_cast<const uint4*>(x2 + pix * C2 + (c0 - C1));
+    const uint4 u = (c0 < C1) ? *reinterpret_cast<const uint4*>(x1n + pix * C1 + c0)
+                              : *reinterpret_cast<const uint4*>(x2n + pix * C2 + (c0 - C1));
     float f[8]; unpack8(u, f, bf);
-    float ga[8], be[8];
-    unpack8(*reinterpret_cast<const uint4*>(gamma + c0), ga, bf);
-    unpack8(*reinterpret_cast<const uint4*>(beta + c0), be, bf);
+    const float4 s0 = *reinterpret_cast<const float4*>(aff + c0), s1 = *reinterpret_cast<const float4*>(aff + c0 + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(aff + C + c0), h1 = *reinterpret_cast<const float4*>(aff + C + c0 + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int g = (c0 + k) / cpg;
-      const float sm = sums[((size_t)n * groups + g) * 2], sq = sums[((size_t)n * groups + g) * 2 + 1];
-      const float mean = sm * inv_n;
-      const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
-      float v = (f[k] - mean) * rsqrtf(var + eps) * ga[k] + be[k];
+      const float v = fmaf(f[k], sc[k], sh[k]);
       f[k] = do_silu ? silu_f(v) : v;
     }
-    *reinterpret_cast<uint4*>(y + pix * C + c0) = pack8(f, bf);
+    *reinterpret_cast<uint4*>(yn + pix * C + c0) = pack8(f, bf);
   }
+  (void)total_vec;
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm

@@ -249,12 +249,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
               }
               if (g.epi == EPI_QKV && col0 >= g.n_split) {
                 const int b = int(grow / g.ntok), tok = int(grow - (long long)b * g.ntok);
+          const size_t vC = (size_t)g.heads * g.hdim;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   const int vc = col0 + j - g.n_split;
                   if (full || col0 + j < g.N) {
-                    const int h = vc / g.hdim, dd = vc - h * g.hdim;
-                    store16(g.Vt, ((size_t)(b * g.heads + h) * g.hdim + dd) * g.ntok + tok, v[j], bf);
+                    store16(g.Vt, ((size_t)b * vC + vc) * g.ntok + tok, v[j], bf);   // (b*heads + h)*hdim + dd == b*C + vc
                   }
                 }
               } else {
