@@ -72,7 +72,9 @@ __device__ __forceinline__ float gelu_erf(float x) {
   p = fmaf(t, p, 0.0705230784f);
   p = fmaf(t, p, 1.0f);
   p = p * p; p = p * p; p = p * p; p = p * p;
-  const float e = 1.0f - __frcp_rn(p);
+  float rp;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rp) : "f"(p));
+  const float e = 1.0f - rp;
   return 0.5f * x * (1.0f + copysignf(e, x));
 }
 
