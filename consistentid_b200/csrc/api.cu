@@ -12,9 +12,11 @@
 #include "../../include/cidb200.h"
 #include "attn_tc.cuh"
 #include "attn_tc2.cuh"
+#include "attn_tc3.cuh"
 #include "elementwise.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
+#include "gemm_tc3.cuh"
 
 using namespace cid;
 
@@ -99,12 +101,12 @@ int num_sms() {
   }
   return g_num_sms;
 }
-// 1 = one-tile-per-CTA kernel (gemm_tc.cuh), 2 = persistent kernel with double-buffered TMEM (gemm_tc2.cuh, default)
+// 1 = one-tile-per-CTA kernel (gemm_tc.cuh), 2 = persistent 1-CTA kernel (gemm_tc2.cuh), 3 = persistent 2-CTA pairs (gemm_tc3.cuh, default)
 int g_gemm_version = 0;
 int gemm_version() {
   if (g_gemm_version == 0) {
     const char* e = getenv("CID_GEMM_VERSION");
-    g_gemm_version = (e && e[0] == '1') ? 1 : 2;
+    g_gemm_version = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 3;
   }
   return g_gemm_version;
 }
@@ -126,8 +128,36 @@ int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap
   return 0;
 }
 
+template <int BN, int STAGES>
+int launch_gemm3(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
+  using SM = Gemm3Smem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    int rc = set_smem(gemm_tc3_kernel<BN, STAGES>, SM::TOTAL, "gemm_tc3_kernel");
+    if (rc) return rc;
+    configured = true;
+  }
+  const int n_tiles = (g.N + BN - 1) / BN;
+  const int total = n_tiles * ((m_tiles + 1) / 2);            // 256-row pair tiles
+  const int max_pairs = num_sms() / 2;
+  const int pairs = total < max_pairs ? total : max_pairs;
+  gemm_tc3_kernel<BN, STAGES><<<2 * pairs, GEMM2_THREADS, SM::TOTAL, st>>>(a1, a2, b, g, n_tiles, total);
+  CID_CHECK_LAUNCH("gemm_tc3_kernel");
+  return 0;
+}
+// rows of B staged per CTA (= TMA box height of the weight map)
+int b_box_rows(int bn) { return (gemm_version() == 3 && bn >= 32) ? bn / 2 : bn; }
+
 int dispatch_gemm(int bn, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
-  if (gemm_version() == 2) {
+  if (gemm_version() == 3 && bn >= 32) {
+    switch (bn) {
+      case 256: return launch_gemm3<256, 6>(a1, a2, b, g, m_tiles, st);
+      case 160: return launch_gemm3<160, 7>(a1, a2, b, g, m_tiles, st);
+      case 64: return launch_gemm3<64, 8>(a1, a2, b, g, m_tiles, st);
+    }
+    return fail(CID_ERR_UNSUPPORTED, "no 2-CTA GEMM instantiation for tile N %d", bn);
+  }
+  if (gemm_version() >= 2) {
     switch (bn) {
       case 256: return launch_gemm2<256, 4>(a1, a2, b, g, m_tiles, st);
       case 160: return launch_gemm2<160, 5>(a1, a2, b, g, m_tiles, st);
@@ -167,7 +197,7 @@ int launch_attn_self(const CUtensorMap& q, const CUtensorMap& k, const CUtensorM
 }
 int g_attn_version = 0;
 int attn_version() {
-  if (g_attn_version == 0) { const char* e = getenv("CID_ATTN_VERSION"); g_attn_version = (e && e[0] == '1') ? 1 : 2; }
+  if (g_attn_version == 0) { const char* e = getenv("CID_ATTN_VERSION"); g_attn_version = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 3; }
   return g_attn_version;
 }
 template <int D_PAD>
@@ -178,6 +208,16 @@ int launch_attn_self2(const CUtensorMap& q, const CUtensorMap& k, const CUtensor
   dim3 grid((a.Nq + 127) / 128, a.H, a.B);
   attn_self2_kernel<D_PAD><<<grid, ATTN_THREADS, C::TOTAL, st>>>(q, k, v, a);
   CID_CHECK_LAUNCH("attn_self2_kernel");
+  return 0;
+}
+template <int D_PAD>
+int launch_attn_self3(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
+  using C = Attn2Cfg<D_PAD>;
+  static bool configured = false;
+  if (!configured) { int rc = set_smem(attn_self3_kernel<D_PAD>, C::TOTAL, "attn_self3_kernel"); if (rc) return rc; configured = true; }
+  dim3 grid((a.Nq + 127) / 128, a.H, a.B);
+  attn_self3_kernel<D_PAD><<<grid, ATTN_THREADS, C::TOTAL, st>>>(q, k, v, a);
+  CID_CHECK_LAUNCH("attn_self3_kernel");
   return 0;
 }
 template <int D_PAD>
@@ -216,7 +256,7 @@ int cid_gemm_tile_n(int N, int epi) {
   // 256-wide tiles cut the L2->SMEM bytes per FLOP (the limiter of the 128x160 tile) wherever the width allows
   static int allow256 = -1;
   if (allow256 < 0) { const char* e = getenv("CID_GEMM_NO256"); allow256 = (e && e[0] == '1') ? 0 : 1; }
-  if (allow256 && gemm_version() == 2 && N % 256 == 0 && N >= 1024) return 256;
+  if (allow256 && gemm_version() >= 2 && N % 256 == 0 && N >= 1024) return 256;
   if (epi == CID_EPI_GEGLU) {
     if (N % 160 == 0) return 160;
     if (N % 64 == 0) return 64;
@@ -243,7 +283,7 @@ int cid_gemm(const void* A, long long lda, const void* A2, long long lda2, int K
   int rc;
   if ((rc = map_2d(&ta1, A, K1, M, lda, 128))) return rc;
   if (K2 > 0) { if ((rc = map_2d(&ta2, A2, K2, M, lda2, 128))) return rc; } else ta2 = ta1;
-  if ((rc = map_2d(&tb, B, K1 + K2, N, K1 + K2, bn))) return rc;
+  if ((rc = map_2d(&tb, B, K1 + K2, N, K1 + K2, b_box_rows(bn)))) return rc;
   GemmArgs g{};
   g.M = M; g.N = N; g.kblocks_a1 = K1 / 64; g.kblocks_a2 = K2 / 64; g.taps = 1; g.a_mode = A_GEMM;
   g.C = C; g.ldc = ldc; g.bias = bias; g.residual = residual; g.ldr = ldr;
@@ -283,7 +323,7 @@ int cid_conv3x3(const void* X, const void* Wt, void* Y, long long ldy, int NB, i
     cuuint32_t box[5] = {64, cuuint32_t(g.TW), cuuint32_t(g.TH), 1, cuuint32_t(g.TN)};
     if ((rc = make_map(&ta, X, 5, dims, str, box))) return rc;
   }
-  if ((rc = map_2d(&tb, Wt, 9LL * Cin, Cout, 9LL * Cin, bn))) return rc;
+  if ((rc = map_2d(&tb, Wt, 9LL * Cin, Cout, 9LL * Cin, b_box_rows(bn)))) return rc;
   g.M = NB * H * W; g.N = Cout; g.kblocks_a1 = Cin / 64; g.kblocks_a2 = 0; g.taps = 9;
   g.a_mode = stride2 ? A_CONV_S2 : A_CONV; g.W = W; g.H = H; g.NB = NB;
   g.C = Y; g.ldc = ldy; g.bias = bias; g.residual = residual; g.ldr = ldr;
@@ -305,6 +345,16 @@ int cid_attn_self(const void* Q, long long q_pitch, const void* K, long long k_p
   AttnArgs a{}; a.B = B; a.H = H; a.Nq = N; a.Nkv = N; a.d = d; a.scale_log2 = 1.4426950408889634f / sqrtf(float(d));
   a.O = O; a.ldo = ldo; a.is_bf16 = dtype == CID_BF16;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (attn_version() == 3) {
+    switch (dp) {
+      case 32: return launch_attn_self3<32>(tq, tk, tv, a, st);
+      case 48: return launch_attn_self3<48>(tq, tk, tv, a, st);
+      case 64: return launch_attn_self3<64>(tq, tk, tv, a, st);
+      case 80: return launch_attn_self3<80>(tq, tk, tv, a, st);
+      case 128: return launch_attn_self3<128>(tq, tk, tv, a, st);
+      case 160: return launch_attn_self3<160>(tq, tk, tv, a, st);
+    }
+  }
   if (attn_version() == 2) {
     switch (dp) {
       case 32: return launch_attn_self2<32>(tq, tk, tv, a, st);

@@ -1,0 +1,273 @@
+// attn_self3_kernel - v3 of the flash self-attention (same operands / results as v1/v2).
+//
+// Measurement that drives this version: v2 cut the softmax instruction count by >2x but the kernel got only 9 % faster, and
+// the per-tile time (~2300 cycles / SM) matches the TMEM READ traffic (two passes over the 64 KB score tile + P.V + row
+// sums per tile at ~64 B/clk/SM), not the ALU work.  v3 therefore minimises tcgen05.ld traffic:
+//   * the 128 scores of a row are read ONCE per tile (4 x LDTM.x32 back to back, one wait) and kept in registers;
+//   * O = sum_j P_j V_j and l = sum_j P_j 1 are ACCUMULATED IN TMEM by the tensor core across all key tiles; the softmax
+//     warps touch them only to rescale, and rescaling is lazy (FlashAttention-4 style): P is computed against a stale
+//     row max m_use, which is refreshed (O, l multiplied by 2^((m_use - m_new) c) via tcgen05.ld/st) only when the true max
+//     has grown by more than 2^8 - so exp() values stay <= 256 (exact in fp16/bf16 range) and rescales are rare;
+//   * O and l are read once, at the end, for the normalisation.
+// The MMA warp also pre-computes its shared-memory descriptors (one IADD per MMA instead of a descriptor build).
+#pragma once
+#include "attn_tc2.cuh"
+
+namespace cid {
+
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// SW128 K-major descriptor split into a constant high word and an address-dependent low word
+constexpr uint32_t DESC_SW128_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_make(uint32_t lo) { return (uint64_t(DESC_SW128_HI) << 32) | lo; }
+
+constexpr float ATTN_RESCALE_THRESHOLD = 8.0f;      // log2 units
+
+template <int D_PAD>
+__global__ void __launch_bounds__(ATTN_THREADS, Attn2Cfg<D_PAD>::MIN_CTAS)
+attn_self3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmVt, const AttnArgs a) {
+  using C = Attn2Cfg<D_PAD>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if ((sbase & 1023u) != 0) { if (threadIdx.x == 0) printf("cid: attn smem base not 1024-aligned\n"); __trap(); }
+  const uint32_t bar0 = sbase + C::OFF_BAR;
+  const uint32_t q_full = bar0;
+  auto k_full = [&](int s) { return bar0 + 8u * (1 + s); };
+  auto k_empty = [&](int s) { return bar0 + 8u * (1 + STAGES + s); };
+  auto v_full = [&](int s) { return bar0 + 8u * (1 + 2 * STAGES + s); };
+  auto v_empty = [&](int s) { return bar0 + 8u * (1 + 3 * STAGES + s); };
+  const uint32_t s_full = bar0 + 8u * (1 + 4 * STAGES);
+  const uint32_t s_free = s_full + 8u;
+  const uint32_t p_full = s_full + 16u;
+  const uint32_t pv_full = s_full + 24u;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + C::OFF_BAR + 8 * (6 + 4 * STAGES));
+
+  const int warp = warp_id(), lane = lane_id();
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int T = (a.Nkv + 127) / 128;
+  const int bf = a.is_bf16;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmVt); }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int s = 0; s < STAGES; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
+      mbar_init(s_full, 1); mbar_init(s_free, 128); mbar_init(p_full, 128); mbar_init(pv_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<C::TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  }
+  if (warp == 2) {
+    reinterpret_cast<uint32_t*>(smem_raw + C::OFF_ONES)[lane] = bf ? 0x3F803F80u : 0x3C003C00u;
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_S = tmem, tmem_O = tmem + 128, tmem_L = tmem + 128 + D_PAD;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, C::Q_BYTES);
+      for (int ch = 0; ch < C::NCH; ++ch) tma_load_4d(sbase + ch * 16384, &tmQ, q_full, ch * 64, q0, h, b);
+      int stage = 0; uint32_t phase = 0;
+      for (int j = 0; j < T; ++j) {
+        const int k0 = j * 128;
+        mbar_wait(k_empty(stage), phase ^ 1u);
+        mbar_expect_tx(k_full(stage), C::K_BYTES);
+        for (int ch = 0; ch < C::NCH; ++ch)
+          tma_load_4d(sbase + C::OFF_K + stage * C::K_BYTES + ch * 16384, &tmK, k_full(stage), ch * 64, k0, h, b);
+        mbar_wait(v_empty(stage), phase ^ 1u);
+        mbar_expect_tx(v_full(stage), C::V_BYTES);
+        for (int kc = 0; kc < 2; ++kc)
+          tma_load_3d(sbase + C::OFF_V + stage * C::V_BYTES + kc * C::V_CHUNK, &tmVt, v_full(stage), k0 + kc * 64, 0, b * a.H + h);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    const uint32_t idesc_s = make_idesc(128, 128, bf);
+    const uint32_t idesc_pv = make_idesc(128, D_PAD, bf);
+    const uint32_t idesc_l = make_idesc(128, 16, bf);
+    const uint64_t ones_desc = make_desc_alias128(sbase + C::OFF_ONES);
+    const uint32_t q_lo = desc_lo(sbase), k_lo = desc_lo(sbase + C::OFF_K), v_lo = desc_lo(sbase + C::OFF_V), p_lo = desc_lo(sbase + C::OFF_P);
+    auto issue_S = [&](int stage) {
+      const uint32_t kl = k_lo + uint32_t(stage * C::K_BYTES) / 16;
+#pragma unroll
+      for (int ch = 0; ch < C::NCH; ++ch) {
+        const int ksteps = (D_PAD - ch * 64 >= 64) ? 4 : (D_PAD - ch * 64) / 16;
+#pragma unroll
+        for (int kk = 0; kk < ksteps; ++kk)
+          umma_ss(tmem_S, desc_make(q_lo + ch * 1024 + kk * 2), desc_make(kl + ch * 1024 + kk * 2), idesc_s, (ch | kk) ? 1u : 0u);
+      }
+    };
+    mbar_wait(q_full, 0);
+    int stage = 0; uint32_t phase = 0;
+    int nstage = 0; uint32_t nphase = 0;
+    mbar_wait(k_full(0), 0);
+    tc_fence_after();
+    if (lane == 0) { issue_S(0); umma_commit(s_full); umma_commit(k_empty(0)); }
+    __syncwarp();
+    if (++nstage == STAGES) { nstage = 0; nphase ^= 1u; }
+    for (int j = 0; j < T; ++j) {
+      if (j + 1 < T) {
+        mbar_wait(k_full(nstage), nphase);
+        mbar_wait(s_free, uint32_t(j & 1));              // the softmax warps hold S_j in registers
+        tc_fence_after();
+        if (lane == 0) { issue_S(nstage); umma_commit(s_full); umma_commit(k_empty(nstage)); }
+        __syncwarp();
+        if (++nstage == STAGES) { nstage = 0; nphase ^= 1u; }
+      }
+      mbar_wait(p_full, uint32_t(j & 1));                // P_j in smem, O / l rescaled if needed
+      mbar_wait(v_full(stage), phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t vl = v_lo + uint32_t(stage * C::V_BYTES) / 16;
+        const uint32_t acc0 = j > 0 ? 1u : 0u;
+#pragma unroll
+        for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t pdesc = desc_make(p_lo + kc * 1024 + kk * 2);
+            const uint32_t acc = (kc | kk) ? 1u : acc0;
+            umma_ss(tmem_O, pdesc, desc_make(vl + kc * (C::V_CHUNK / 16) + kk * 2), idesc_pv, acc);
+            umma_ss(tmem_L, pdesc, ones_desc, idesc_l, acc);
+          }
+        umma_commit(pv_full);
+        umma_commit(v_empty(stage));
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    }
+  } else {
+    // ============================================================ softmax + output (warps 2..5, one query row per thread)
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = uint32_t(quarter * 32) << 16;
+    uint8_t* sP = smem_raw + C::OFF_P;
+    const float c = a.scale_log2;
+    float m_use = -INFINITY;                              // row max baked into O, l and used for P
+
+    for (int j = 0; j < T; ++j) {
+      const int kvalid = a.Nkv - j * 128;
+      mbar_wait(s_full, uint32_t(j & 1));
+      tc_fence_after();
+      uint32_t v[128];
+      {
+        uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+        uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+        uint32_t (&v2)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[64]);
+        uint32_t (&v3)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[96]);
+        tmem_ld_x32(tmem_S + lane_off + 0, v0);
+        tmem_ld_x32(tmem_S + lane_off + 32, v1);
+        tmem_ld_x32(tmem_S + lane_off + 64, v2);
+        tmem_ld_x32(tmem_S + lane_off + 96, v3);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      mbar_arrive(s_free);                                // S_j lives in registers now: S_{j+1} may be computed
+      if (kvalid < 128) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) if (i >= kvalid) v[i] = 0xff800000u;       // -inf
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; i += 2) mx = max3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+      const float m_new = fmaxf(m_use, mx);
+      const bool need = (m_new - m_use) * c > ATTN_RESCALE_THRESHOLD;            // also true on the first tile (m_use = -inf)
+      if (j > 0) {
+        mbar_wait(pv_full, uint32_t((j - 1) & 1));        // P.V_{j-1} retired: P smem reusable, O / l quiescent
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+          const float f = need ? fast_exp2((m_use - m_new) * c) : 1.0f;
+#pragma unroll
+          for (int cc = 0; cc < D_PAD + 16; cc += 16) {   // O columns then the 16 row-sum columns (contiguous in TMEM)
+            uint32_t t[16];
+            tmem_ld_x16(tmem_O + lane_off + cc, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * f);
+            tmem_st_x16(tmem_O + lane_off + cc, t);
+          }
+          tmem_st_wait();
+        }
+      }
+      if (need) m_use = m_new;
+      const float nmc = -m_use * c;
+      // P = 2^((s - m_use) c), packed, straight into the swizzled A-operand tile
+#pragma unroll
+      for (int cc = 0; cc < 128; cc += 32) {
+        uint32_t pk[16];
+        if (bf) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2)
+            pk[i >> 1] = ex2_pack<1>(fmaf(__uint_as_float(v[cc + i]), c, nmc), fmaf(__uint_as_float(v[cc + i + 1]), c, nmc));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2)
+            pk[i >> 1] = ex2_pack<0>(fmaf(__uint_as_float(v[cc + i]), c, nmc), fmaf(__uint_as_float(v[cc + i + 1]), c, nmc));
+        }
+        uint8_t* tile = sP + (cc >> 6) * 16384;
+        const int col = cc & 63;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          st_sw128(tile, r, col + q * 8, make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]));
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // ---- normalise and store
+    mbar_wait(pv_full, uint32_t((T - 1) & 1));
+    tc_fence_after();
+    float l;
+    {
+      uint32_t t[16];
+      tmem_ld_x16(tmem_L + lane_off, t);
+      tmem_ld_wait();
+      l = __uint_as_float(t[0]);
+    }
+    const float inv = 1.f / l;
+    const bool row_ok = q0 + r < a.Nq;
+    uint16_t* dst = reinterpret_cast<uint16_t*>(a.O) + ((long long)b * a.Nq + q0 + r) * a.ldo + h * a.d;
+#pragma unroll
+    for (int cc = 0; cc < D_PAD; cc += 16) {
+      uint32_t t[16];
+      tmem_ld_x16(tmem_O + lane_off + cc, t);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (cc + q * 8 < a.d) {
+            uint4 u;
+            u.x = pack16(__uint_as_float(t[q * 8 + 0]) * inv, __uint_as_float(t[q * 8 + 1]) * inv, bf);
+            u.y = pack16(__uint_as_float(t[q * 8 + 2]) * inv, __uint_as_float(t[q * 8 + 3]) * inv, bf);
+            u.z = pack16(__uint_as_float(t[q * 8 + 4]) * inv, __uint_as_float(t[q * 8 + 5]) * inv, bf);
+            u.w = pack16(__uint_as_float(t[q * 8 + 6]) * inv, __uint_as_float(t[q * 8 + 7]) * inv, bf);
+            *reinterpret_cast<uint4*>(dst + cc + q * 8) = u;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<C::TMEM_COLS>(tmem); }
+}
+
+}  // namespace cid
