@@ -101,12 +101,13 @@ int num_sms() {
   }
   return g_num_sms;
 }
-// 1 = one-tile-per-CTA kernel (gemm_tc.cuh), 2 = persistent 1-CTA kernel (gemm_tc2.cuh), 3 = persistent 2-CTA pairs (gemm_tc3.cuh, default)
+// 1 = one-tile-per-CTA kernel (gemm_tc.cuh), 2 = persistent 1-CTA kernel (gemm_tc2.cuh, default),
+// 3 = persistent 2-CTA pairs (gemm_tc3.cuh; parity-green, measured no faster than 2 on B200 - see DESIGN.md)
 int g_gemm_version = 0;
 int gemm_version() {
   if (g_gemm_version == 0) {
     const char* e = getenv("CID_GEMM_VERSION");
-    g_gemm_version = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 3;
+    g_gemm_version = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 2;
   }
   return g_gemm_version;
 }
@@ -444,8 +445,12 @@ int cid_gn_apply(const void* x1, int C1, const void* x2, int C2, int NB, int HW,
 int cid_layernorm(const void* x, const void* gamma, const void* beta, void* y, long long rows, int C, float eps, int dtype, void* stream) {
   if (!x || !gamma || !beta || !y || C % 8 || C > 2048) return fail(CID_ERR_ARG, "cid_layernorm: C=%d must be a multiple of 8 and <= 2048", C);
   const int rows_per_block = 8;
-  layernorm_kernel<<<(unsigned)((rows + rows_per_block - 1) / rows_per_block), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      (const uint16_t*)x, (const uint16_t*)gamma, (const uint16_t*)beta, (uint16_t*)y, rows, C, eps, dtype == CID_BF16);
+  const unsigned grid = (unsigned)((rows + rows_per_block - 1) / rows_per_block);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int maxv = (C / 8 + 31) / 32;
+#define CID_LN(MV) layernorm_kernel<MV><<<grid, 256, 0, st>>>((const uint16_t*)x, (const uint16_t*)gamma, (const uint16_t*)beta, (uint16_t*)y, rows, C, eps, dtype == CID_BF16)
+  if (maxv <= 1) CID_LN(1); else if (maxv <= 2) CID_LN(2); else if (maxv <= 3) CID_LN(3); else if (maxv <= 5) CID_LN(5); else CID_LN(8);
+#undef CID_LN
   CID_CHECK_LAUNCH("layernorm_kernel");
   return 0;
 }

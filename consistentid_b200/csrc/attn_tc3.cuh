@@ -25,10 +25,6 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// SW128 K-major descriptor split into a constant high word and an address-dependent low word
-constexpr uint32_t DESC_SW128_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
-__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
-__device__ __forceinline__ uint64_t desc_make(uint32_t lo) { return (uint64_t(DESC_SW128_HI) << 32) | lo; }
 
 constexpr float ATTN_RESCALE_THRESHOLD = 8.0f;      // log2 units
 

@@ -151,6 +151,12 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
   return d;
 }
 
+// the same descriptor split into a constant high word and an address-dependent low word: stepping a descriptor through
+// k-slices / stages is then ONE integer add (the MMA-issuing thread is a serial bottleneck: keep its instruction count low)
+constexpr uint32_t DESC_SW128_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_make(uint32_t lo) { return (uint64_t(DESC_SW128_HI) << 32) | lo; }
+
 // TMEM -> registers: this warp's 32 lanes x N consecutive 32-bit columns (thread i <- lane base+i)
 __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

@@ -42,7 +42,21 @@ gn_stats_kernel(const uint16_t* __restrict__ x1, int C1, const uint16_t* __restr
     const bool first = c0 < C1;
     const uint16_t* src = first ? x1 + (size_t)n * HW * C1 + c0 : x2 + (size_t)n * HW * C2 + (c0 - C1);
     const int pitch = first ? C1 : C2;
-    for (int p = blockIdx.x * tpp + prow; p < HW; p += gridDim.x * tpp) {
+    // 4 independent 16-byte loads in flight per thread (the pass is pure HBM streaming)
+    const int pstride = gridDim.x * tpp;
+    int p = blockIdx.x * tpp + prow;
+    for (; p + 3 * pstride < HW; p += 4 * pstride) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(src + (size_t)(p + k * pstride) * pitch);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8]; unpack8(u[k], f, bf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+      }
+    }
+    for (; p < HW; p += pstride) {
       uint4 u = *reinterpret_cast<const uint4*>(src + (size_t)p * pitch);
       float f[8]; unpack8(u, f, bf);
 #pragma unroll
@@ -110,7 +124,9 @@ gn_apply_kernel(const uint16_t* __restrict__ x1, int C1, const uint16_t* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
-// one warp per row, C <= 2048, C % 8 == 0
+// one warp per row, C <= 2048, C % 8 == 0; MAXV = ceil(C / 256) vectors per lane (templated: registers -> occupancy,
+// the kernel is a latency-bound streaming pass)
+template <int MAXV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ gamma, const uint16_t* __restrict__ beta,
                  uint16_t* __restrict__ y, long long rows, int C, float eps, int bf) {
@@ -118,7 +134,6 @@ layernorm_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ ga
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
   const int V = C / 8;
-  constexpr int MAXV = 8;                        // 8 vectors * 32 lanes * 8 = 2048 channels
   float f[MAXV][8];
   float s = 0.f;
 #pragma unroll

@@ -172,6 +172,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     const uint32_t idesc = make_idesc(2 * GEMM_BM, BN, g.is_bf16);
     int stage = 0; uint32_t phase = 0;
     int it = 0;
+    const uint32_t a_lo0 = desc_lo(smem_base);
     if (rank == 0)
     for (int tile = pair; tile < total_tiles; tile += num_pairs, ++it) {
       const int ab = it & 1;
@@ -179,21 +180,21 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
       mbar_wait(acc_empty(ab), aphase ^ 1u);              // epilogue has drained this accumulator (first use: free)
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + ab * ACC_STRIDE;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full_bar(stage), phase);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_base + stage * SM::STAGE_BYTES;
-          const uint32_t sb = sa + SM::A_BYTES;
+      if (lane == 0) {                                     // one thread runs the whole issue loop (no per-k-block warp sync)
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + uint32_t(stage) * uint32_t(SM::STAGE_BYTES / 16);
+          const uint32_t b_lo = a_lo + uint32_t(SM::A_BYTES / 16);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_ss_2cta(tmem_acc, make_desc_sw128(sa + k * 32), make_desc_sw128(sb + k * 32), idesc, (kb | k) ? 1u : 0u);
+            umma_ss_2cta(tmem_acc, desc_make(a_lo + k * 2), desc_make(b_lo + k * 2), idesc, (kb | k) ? 1u : 0u);
           umma_commit_2cta(empty_bar(stage));
           if (kb == num_kb - 1) umma_commit_2cta(acc_full(ab));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      stage = __shfl_sync(0xffffffffu, stage, 0); phase = __shfl_sync(0xffffffffu, phase, 0);
     }
   } else {
     // ================================================================ epilogue (warps 2..9)
