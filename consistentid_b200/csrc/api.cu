@@ -380,7 +380,7 @@ int cid_attn_self(const void* Q, long long q_pitch, const void* K, long long k_p
 int cid_attn_cross(const void* Q, long long q_pitch, const void* Kcat, const void* Vtcat, void* O, long long ldo, int B, int H,
                    int N, int d, int n_text, int n_ip, float ip_scale, int dtype, void* stream) {
   if (!Q || !Kcat || !Vtcat || !O || B <= 0 || H <= 0 || N <= 0) return fail(CID_ERR_ARG, "cid_attn_cross: null pointer or empty problem");
-  if (n_text <= 0 || n_text > 80 || n_ip < 0 || n_ip > 16) return fail(CID_ERR_UNSUPPORTED, "cid_attn_cross: n_text=%d (<=80), n_ip=%d (<=16)", n_text, n_ip);
+  if (n_text <= 0 || n_text > (n_ip > 0 ? 80 : 96) || n_ip < 0 || n_ip > 16) return fail(CID_ERR_UNSUPPORTED, "cid_attn_cross: n_text=%d (<=80, or <=96 without id tokens), n_ip=%d (<=16)", n_text, n_ip);
   const int dp = d_pad_for(d);
   if (dp < 0) return fail(CID_ERR_UNSUPPORTED, "cid_attn_cross: head dim %d unsupported", d);
   CUtensorMap tq, tk, tv; int rc;
@@ -404,7 +404,7 @@ int cid_attn_cross(const void* Q, long long q_pitch, const void* Kcat, const voi
 int cid_pack_cross_kv(const void* k_text, const void* v_text, const void* k_ip, const void* v_ip, void* k_cat, void* vt_cat,
                       int B, int C, int heads, int n_text, int n_ip, void* stream) {
   if (!k_text || !v_text || !k_cat || !vt_cat || (n_ip > 0 && (!k_ip || !v_ip))) return fail(CID_ERR_ARG, "cid_pack_cross_kv: null pointer");
-  if (n_text > 80 || n_ip > 16 || C % heads) return fail(CID_ERR_ARG, "cid_pack_cross_kv: bad sizes");
+  if (n_text > (n_ip > 0 ? 80 : 96) || n_ip > 16 || C % heads) return fail(CID_ERR_ARG, "cid_pack_cross_kv: bad sizes");
   const long long total = (long long)B * 96 * C;
   pack_cross_kv_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       (const uint16_t*)k_text, (const uint16_t*)v_text, (const uint16_t*)k_ip, (const uint16_t*)v_ip, (uint16_t*)k_cat,
@@ -488,6 +488,20 @@ int cid_add_inplace(void* y, const void* x, long long n_elems, int dtype, void* 
   CID_CHECK_LAUNCH("add_inplace_kernel");
   return 0;
 }
+int cid_silu_inplace(void* y, long long n_elems, int dtype, void* stream) {
+  if (!y || n_elems % 8) return fail(CID_ERR_ARG, "cid_silu_inplace: n_elems must be a multiple of 8");
+  silu_inplace_kernel<<<grid_for(n_elems / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>((uint4*)y, n_elems / 8, dtype == CID_BF16);
+  CID_CHECK_LAUNCH("silu_inplace_kernel");
+  return 0;
+}
+int cid_inpaint_blend(float* x, void* x16, const float* image_latents, const float* noise, const float* mask, int B, int HW,
+                      const float* blend_table, const int* step_dev, int dtype, void* stream) {
+  if (!x || !x16 || !image_latents || !noise || !mask || !blend_table || !step_dev) return fail(CID_ERR_ARG, "cid_inpaint_blend: null pointer");
+  inpaint_blend_kernel<<<grid_for((long long)B * 4 * HW, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, (uint16_t*)x16, image_latents, noise, mask, B, HW, blend_table, step_dev, dtype == CID_BF16);
+  CID_CHECK_LAUNCH("inpaint_blend_kernel");
+  return 0;
+}
 int cid_timestep_embed(const float* t_dev, int t_stride, int rows, int dim, void* out, long long ld, int col0, int dtype, void* stream) {
   if (!t_dev || !out || dim % 2) return fail(CID_ERR_ARG, "cid_timestep_embed: bad arguments");
   timestep_embed_kernel<<<grid_for((long long)rows * dim / 2, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(t_dev, t_stride, rows, dim, (uint16_t*)out, ld, col0, dtype == CID_BF16);
@@ -512,9 +526,10 @@ int cid_cfg_sched_step(const void* eps, int ld_eps, float* x, float* x0_prev, vo
   CID_CHECK_LAUNCH("cfg_sched_step_kernel");
   return 0;
 }
-int cid_latents_to_input(const float* x, void* next_in, int CP, int B, int HW, const float* coef_table, int dtype, void* stream) {
-  if (!x || !next_in || !coef_table || CP % 8) return fail(CID_ERR_ARG, "cid_latents_to_input: bad arguments");
-  latents_to_input_kernel<<<grid_for((long long)B * HW, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, (uint16_t*)next_in, CP, B, HW, coef_table, dtype == CID_BF16);
+int cid_latents_to_input(const float* x, void* next_in, int CP, int B, int HW, const float* coef_table, const int* step_dev, int nsteps,
+                         int keep_ch4_up, int dtype, void* stream) {
+  if (!x || !next_in || !coef_table || CP % 8 || nsteps <= 0) return fail(CID_ERR_ARG, "cid_latents_to_input: bad arguments");
+  latents_to_input_kernel<<<grid_for((long long)B * HW, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, (uint16_t*)next_in, CP, B, HW, coef_table, step_dev, nsteps, keep_ch4_up, dtype == CID_BF16);
   CID_CHECK_LAUNCH("latents_to_input_kernel");
   return 0;
 }

@@ -290,11 +290,16 @@ struct CrossCfg {
   static constexpr int V_BYTES = 2 * V_CHUNK;
   static constexpr int OFF_K = Q_BYTES;
   static constexpr int OFF_V = OFF_K + K_BYTES;
-  static constexpr int OFF_P = OFF_V + V_BYTES;
-  static constexpr int OFF_BAR = OFF_P + 2 * 16384;
+  // P (A operand of the second MMAs) re-uses memory that is dead once S = Q K^T has been read: chunk 0 (keys 0-63) lives
+  // in Q's first 16 KB, chunk 1 (keys 64-95) in Q's second chunk when the head dim has one, else in its own 16 KB.
+  // O_text / O_ip accumulators likewise overwrite the S columns of TMEM.  -> 56-60 KB smem, 128 TMEM columns for
+  // head dims <= 64: three CTAs per SM instead of two for this latency-bound kernel.
+  static constexpr int OFF_P0 = 0;
+  static constexpr int OFF_P1 = (NCH >= 2) ? 16384 : OFF_V + V_BYTES;
+  static constexpr int OFF_BAR = (NCH >= 2) ? OFF_V + V_BYTES : OFF_V + V_BYTES + 16384;
   static constexpr int TOTAL = OFF_BAR + 64;
-  static constexpr int TMEM_COLS = (128 + 2 * D_PAD <= 256) ? 256 : 512;
-  static constexpr int MIN_CTAS = (TMEM_COLS == 256) ? 2 : 1;
+  static constexpr int TMEM_COLS = (2 * D_PAD <= 128) ? 128 : (2 * D_PAD <= 256) ? 256 : 512;
+  static constexpr int MIN_CTAS = (TMEM_COLS == 128) ? 3 : (TMEM_COLS == 256) ? 2 : 1;
 };
 
 template <int D_PAD>
@@ -322,7 +327,7 @@ attn_cross_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_S = tmem, tmem_Ot = tmem + 128, tmem_Oi = tmem + 128 + D_PAD;
+  const uint32_t tmem_S = tmem, tmem_Ot = tmem, tmem_Oi = tmem + D_PAD;      // O_* overwrite S after the softmax has read it
 
   if (warp == 0 && lane == 0) {
     mbar_expect_tx(bar_ld, C::Q_BYTES + C::K_BYTES + C::V_BYTES);
@@ -367,7 +372,8 @@ attn_cross_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
   }
   float lt = 0.f, li = 0.f;
-  uint8_t* sP = smem_raw + C::OFF_P;
+  uint8_t* sP0 = smem_raw + C::OFF_P0;
+  uint8_t* sP1 = smem_raw + C::OFF_P1;
 #pragma unroll 1
   for (int cc = 0; cc < C::KROWS; cc += 32) {
     uint32_t v[32];
@@ -387,7 +393,7 @@ attn_cross_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       pk[i >> 1] = pack16(p[0], p[1], bf);
     }
-    uint8_t* tile = sP + (cc >> 6) * 16384;
+    uint8_t* tile = (cc >> 6) ? sP1 : sP0;
     const int col = cc & 63;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -399,15 +405,19 @@ attn_cross_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   if (warp == 0 && lane == 0) {
     tc_fence_after();
     const uint32_t idesc_pv = make_idesc(128, D_PAD, a.is_bf16);
-    const uint32_t sp = sbase + C::OFF_P, sv = sbase + C::OFF_V;
-    // text range: keys [0, 80) = 5 k-steps (rows 77..79 of K_cat / V_cat are zero padding, P is 0 there)
+    const uint32_t sp0 = sbase + C::OFF_P0, sp1 = sbase + C::OFF_P1, sv = sbase + C::OFF_V;
+    // text range: keys [0, 80) = 5 k-steps (rows 77..79 of K_cat / V_cat are zero padding, P is 0 there); with no id tokens
+    // (plain cross-attention, e.g. ControlNet's default processor over all 81 rows) the text range spans all 96 rows
+    const int tsteps = (a.n_ip > 0) ? 5 : 6;
 #pragma unroll
-    for (int ks = 0; ks < 5; ++ks) {
-      const int kc = ks >> 2, kk = ks & 3;
-      umma_ss(tmem_Ot, make_desc_sw128(sp + kc * 16384 + kk * 32), make_desc_sw128(sv + kc * C::V_CHUNK + kk * 32), idesc_pv, ks ? 1u : 0u);
+    for (int ks = 0; ks < 6; ++ks) {
+      if (ks < tsteps) {
+        const int kc = ks >> 2, kk = ks & 3;
+        umma_ss(tmem_Ot, make_desc_sw128((kc ? sp1 : sp0) + kk * 32), make_desc_sw128(sv + kc * C::V_CHUNK + kk * 32), idesc_pv, ks ? 1u : 0u);
+      }
     }
     // id range: keys [80, 96) = k-step 5 (chunk 1, second 16-key slice)
-    umma_ss(tmem_Oi, make_desc_sw128(sp + 16384 + 32), make_desc_sw128(sv + C::V_CHUNK + 32), idesc_pv, 0u);
+    if (a.n_ip > 0) umma_ss(tmem_Oi, make_desc_sw128(sp1 + 32), make_desc_sw128(sv + C::V_CHUNK + 32), idesc_pv, 0u);
     umma_commit(bar_o);
   }
   __syncwarp();

@@ -242,6 +242,34 @@ add_inplace_kernel(uint4* __restrict__ y, const uint4* __restrict__ x, long long
   }
 }
 
+// y = silu(y) (ControlNet conditioning-embedding convs)
+__global__ void __launch_bounds__(256)
+silu_inplace_kernel(uint4* __restrict__ y, long long total_vec, int bf) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    float a[8]; unpack8(y[i], a, bf);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = silu_f(a[k]);
+    y[i] = pack8(a, bf);
+  }
+}
+// inpaint latent blending after a scheduler step (pipelines/StableDIffusionControlNetInpaint_ConsistentID.py:437-449):
+//   x = (1 - m) * (ca * image_latents + cn * noise) + m * x,   {ca, cn} = blend_table[step] = add_noise coefficients of the
+//   NEXT timestep ((1, 0) on the last step).  x: fp32 master latents [B,4,HW]; mask [B,1,HW] (1 = repaint).
+__global__ void __launch_bounds__(256)
+inpaint_blend_kernel(float* __restrict__ x, uint16_t* __restrict__ x16, const float* __restrict__ img, const float* __restrict__ noise,
+                     const float* __restrict__ mask, int B, int HW, const float* __restrict__ blend_table, const int* __restrict__ step_ptr, int bf) {
+  const float ca = blend_table[2 * (*step_ptr)], cn = blend_table[2 * (*step_ptr) + 1];
+  const long long total = (long long)B * 4 * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = int(i % HW);
+    const int b = int(i / (4LL * HW));
+    const float m = mask[(size_t)b * HW + p];
+    const float v = (1.f - m) * (ca * img[i] + cn * noise[i]) + m * x[i];
+    x[i] = v;
+    store16(x16, i, v, bf);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ embeddings
 // diffusers get_timestep_embedding(flip_sin_to_cos=True, downscale_freq_shift=0): out[r] = [cos(t*f), sin(t*f)], f_i = 1e4^(-i/half)
 // t values: t_ptr[r * t_stride] (t_stride 0 -> one scalar broadcast to all rows).  Output rounded to 16-bit at
@@ -382,8 +410,10 @@ cfg_sched_step_kernel(const uint16_t* __restrict__ eps, int ld_eps, float* __res
 // first-step helper: fp32 master latents [B,4,HW] -> UNet input NHWC (both CFG halves), times in_scale of step 0
 __global__ void __launch_bounds__(256)
 latents_to_input_kernel(const float* __restrict__ x, uint16_t* __restrict__ next_in, int CP, int B, int HW,
-                        const float* __restrict__ coef_table, int bf) {
-  const float sc = coef_table[6];                // coef[0][6] = in_scale of step 0
+                        const float* __restrict__ coef_table, const int* __restrict__ step_ptr, int nsteps, int vec4_only, int bf) {
+  int st = step_ptr ? *step_ptr : 0;
+  if (st >= nsteps) st = nsteps - 1;
+  const float sc = coef_table[8 * st + 6];       // in_scale of the step about to run
   const long long total = (long long)B * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int b = int(i / HW), p = int(i % HW);
@@ -393,8 +423,13 @@ latents_to_input_kernel(const float* __restrict__ x, uint16_t* __restrict__ next
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) nx[ch] = x[((size_t)b * 4 + ch) * HW + p] * sc;
     const uint4 v = pack8(nx, bf);
-    reinterpret_cast<uint4*>(next_in + ((size_t)b * HW + p) * CP)[0] = v;
-    reinterpret_cast<uint4*>(next_in + ((size_t)(B + b) * HW + p) * CP)[0] = v;
+    if (vec4_only) {                             // 9-channel inpaint UNet: channels 4..8 (mask, masked latents) are static, keep them
+      reinterpret_cast<uint2*>(next_in + ((size_t)b * HW + p) * CP)[0] = make_uint2(v.x, v.y);
+      reinterpret_cast<uint2*>(next_in + ((size_t)(B + b) * HW + p) * CP)[0] = make_uint2(v.x, v.y);
+    } else {
+      reinterpret_cast<uint4*>(next_in + ((size_t)b * HW + p) * CP)[0] = v;
+      reinterpret_cast<uint4*>(next_in + ((size_t)(B + b) * HW + p) * CP)[0] = v;
+    }
   }
 }
 

@@ -51,7 +51,9 @@ _SIGS = {
     "cid_skinny_linear": ([_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp], _i),
     "cid_cfg_sched_step": ([_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _i, _vp], _i),
     "cid_advance_step": ([_vp, _vp, _vp, _i, _vp], _i),
-    "cid_latents_to_input": ([_vp, _vp, _i, _i, _i, _vp, _i, _vp], _i),
+    "cid_latents_to_input": ([_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp], _i),
+    "cid_silu_inplace": ([_vp, _ll, _i, _vp], _i),
+    "cid_inpaint_blend": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp], _i),
 }
 EXPORTS = tuple(_SIGS)
 for _name, (_args, _res) in _SIGS.items():

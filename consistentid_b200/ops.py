@@ -165,8 +165,19 @@ def cfg_sched_step(eps, ld_eps, x, x0_prev, x16, next_in, CP, B, HW, guidance, c
          _p(coef_table), _p(step_dev), _dt(eps), _stream())
 
 
-def latents_to_input(x, next_in, CP, B, HW, coef_table):
-    call("cid_latents_to_input", _p(x), _p(next_in), CP, B, HW, _p(coef_table), _dt(next_in), _stream())
+def latents_to_input(x, next_in, CP, B, HW, coef_table, step_dev=None, nsteps=1, keep_ch4_up=False):
+    call("cid_latents_to_input", _p(x), _p(next_in), CP, B, HW, _p(coef_table), _p(step_dev), nsteps, 1 if keep_ch4_up else 0,
+         _dt(next_in), _stream())
+
+
+def silu_inplace(y):
+    call("cid_silu_inplace", _p(y), y.numel(), _dt(y), _stream())
+    return y
+
+
+def inpaint_blend(x, x16, image_latents, noise, mask, B, HW, blend_table, step_dev):
+    call("cid_inpaint_blend", _p(x), _p(x16), _p(image_latents), _p(noise), _p(mask), B, HW, _p(blend_table), _p(step_dev),
+         _dt(x16), _stream())
 
 
 def advance_step(step_dev, t_dev, ts_table, n):

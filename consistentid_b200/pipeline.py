@@ -70,6 +70,103 @@ class B200Denoiser:
             self._graphs[phase] = g
         g.replay()
 
+    # ------------------------------------------------------------------ ControlNet + inpaint variant (config 5)
+    @torch.no_grad()
+    def controlnet_inpaint(self, controlnet, latents, null_embeds, augmented_embeds, text_embeds, control_image, image_latents,
+                           noise, mask, num_inference_steps=50, guidance_scale=5.0, start_merge_step=0, conditioning_scale=1.0,
+                           masked_image_latents=None):
+        """The reference's ControlNet + inpaint loop (pipelines/StableDIffusionControlNetInpaint_ConsistentID.py:375-449, strength 1):
+        per step ControlNet on the cond half -> residuals into the UNet (both CFG halves) -> CFG + scheduler step -> for the
+        4-channel UNet the latent blend with the re-noised original; a 9-channel UNet instead sees [latents | mask | masked latents].
+        One CUDA-graph replay per step, like ``__call__``.  mask [B,1,h,w]: 1 = repaint."""
+        import numpy as np
+        u, sch = self.unet, self.scheduler
+        dev = u.device
+        B, _, h, w = latents.shape
+        HW, NB = h * w, 2 * B
+        n = num_inference_steps
+        nine = u.spec.in_channels == 9
+        sig = ("cn", B, h, w, n, float(guidance_scale), sch.kind, u.ip_scale, float(conditioning_scale), nine)
+        if sig != self._graph_sig:
+            self._graphs.clear()
+            self._graph_sig = sig
+        u.plan(NB, h, w)
+        controlnet.plan(B, h, w)
+        controlnet.share_timestep(u)
+        sch.set_timesteps(n, device=dev)
+        coef, ts = sch.device_tables(dev)
+        controlnet.set_control_image(control_image)
+        phases, cn_phases = {}, {}
+        for name, pos in (("text", text_embeds), ("aug", augmented_embeds)):
+            if (name == "text" and start_merge_step >= 0) or (name == "aug" and start_merge_step < n - 1):
+                phases[name] = u.set_prompt(self._pair(null_embeds, pos, B), None, key="phase:" + name)
+                pos16 = self._dev16(pos)
+                cn_phases[name] = controlnet.set_prompt(pos16.expand(B, *pos16.shape[1:]).contiguous(), None, key="phase:" + name)
+        # add_noise coefficients of the NEXT timestep for the blend ((1, 0) after the last step)
+        acp = sch.acp
+        blend = np.zeros((n, 2), dtype=np.float32)
+        for i in range(n):
+            if i < n - 1:
+                a = acp[int(sch._ts_host[i + 1])]
+                blend[i] = (np.sqrt(a), np.sqrt(1 - a))
+            else:
+                blend[i] = (1.0, 0.0)
+        st = {"B": B, "HW": HW, "n": n, "guidance": float(guidance_scale), "coef": coef, "ts": ts,
+              "x": u._buf("lat32", (B, 4, HW), torch.float32), "x0": u._buf("lat_x0", (B, 4, HW), torch.float32),
+              "x16": u._buf("lat16", (B, 4, HW)), "step": u._buf("step_dev", (1,), torch.int32),
+              "blend": torch.from_numpy(blend).to(dev), "img": image_latents.reshape(B, 4, HW).to(dev, torch.float32).contiguous(),
+              "noise": noise.reshape(B, 4, HW).to(dev, torch.float32).contiguous(),
+              "mask": mask.reshape(B, 1, HW).to(dev, torch.float32).contiguous()}
+        st["x"].copy_(latents.reshape(B, 4, HW).to(dev, non_blocking=True))
+        st["x0"].zero_(); st["step"].zero_()
+        u._buf("t_dev", (1,), torch.float32).copy_(ts[:1])
+        x_in = u._buf("x_in", (NB * HW, CIN_PAD))
+        if nine:   # static channels 4..8 of the UNet input: mask, masked-image latents (both CFG halves)
+            extra = torch.cat([mask.reshape(B, 1, HW), masked_image_latents.reshape(B, 4, HW)], 1).to(dev, u.dtype)
+            x_in.zero_()
+            x_in.view(2, B, HW, CIN_PAD)[:, :, :, 4:9] = extra.permute(0, 2, 1)[None]
+        ops.latents_to_input(st["x"], x_in, CIN_PAD, B, HW, coef, st["step"], n, keep_ch4_up=nine)
+
+        def step_eager(phase):
+            down, mid = controlnet.forward(x_in[:B * HW], cn_phases[phase], conditioning_scale)
+            eps = u.forward(phases[phase], residuals=(down, mid))
+            ops.cfg_sched_step(eps, 4, st["x"], st["x0"], st["x16"], None, CIN_PAD, B, HW, st["guidance"], coef, st["step"])
+            if not nine:
+                ops.inpaint_blend(st["x"], st["x16"], st["img"], st["noise"], st["mask"], B, HW, st["blend"], st["step"])
+            ops.advance_step(st["step"], u._buf("t_dev", (1,), torch.float32), ts, n)
+            ops.latents_to_input(st["x"], x_in, CIN_PAD, B, HW, coef, st["step"], n, keep_ch4_up=nine)
+
+        def run(phase):
+            if not self.use_cuda_graph:
+                return step_eager(phase)
+            g = self._graphs.get(phase)
+            if g is None:
+                keys = ("x", "x0", "step")
+                snap = {k: st[k].clone() for k in keys}
+                t_dev = u._buf("t_dev", (1,), torch.float32)
+                t_snap, in_snap = t_dev.clone(), x_in.clone()
+                s_ = torch.cuda.Stream()
+                s_.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s_):
+                    step_eager(phase)
+                torch.cuda.current_stream().wait_stream(s_)
+
+                def restore():
+                    for k in keys:
+                        st[k].copy_(snap[k])
+                    t_dev.copy_(t_snap); x_in.copy_(in_snap)
+                restore()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    step_eager(phase)
+                restore()
+                self._graphs[phase] = g
+            g.replay()
+
+        for i in range(n):
+            run("text" if i <= start_merge_step else "aug")
+        return st["x16"].reshape(B, 4, h, w).clone()
+
     # ------------------------------------------------------------------ public API
     @torch.no_grad()
     def __call__(self, latents, null_embeds, augmented_embeds, text_embeds, num_inference_steps=30, guidance_scale=5.0,

@@ -31,29 +31,37 @@ class _Params:
     """Packs every weight the engine needs, in the layout its kernels want, into ONE flat 16-bit arena
     (a single contiguous tensor: one NCCL broadcast moves the whole model, see dist.py)."""
 
-    def __init__(self, spec: UNetSpec, unet_sd, adapter_sd, dtype, device, rank, lora_scale=1.0):
+    def __init__(self, spec: UNetSpec, unet_sd, adapter_sd, dtype, device, rank, lora_scale=1.0, kinds=("down", "mid", "up"),
+                 finalize=True):
+        """``adapter_sd`` None = no ConsistentID adapters (ControlNet keeps diffusers' default processors: no LoRA, no id branch);
+        ``kinds`` selects the block groups that exist (ControlNet = down + mid, no head)."""
         self.spec, self.dtype, self.device = spec, dtype, device
         self._items = {}     # name -> (offset, shape)
         self._staged = []    # (name, tensor) before arena allocation
+        self.kinds = kinds
         ushapes, ashapes = param_shapes(spec, rank)
-        for n, s in ushapes.items():
-            if n not in unet_sd or tuple(unet_sd[n].shape) != s:
-                raise KeyError(f"unet state_dict: missing/mis-shaped '{n}' (want {s})")
-        for n, s in ashapes.items():
-            if n not in adapter_sd or tuple(adapter_sd[n].shape) != s:
-                raise KeyError(f"adapter_modules state_dict: missing/mis-shaped '{n}' (want {s}); keys are positional "
-                               f"'{{i}}.to_q_lora.down.weight' in unet.attn_processors order")
+        is_unet = "up" in kinds
+        if is_unet:
+            for n, s in ushapes.items():
+                if n not in unet_sd or tuple(unet_sd[n].shape) != s:
+                    raise KeyError(f"unet state_dict: missing/mis-shaped '{n}' (want {s})")
+        if adapter_sd is not None:
+            for n, s in ashapes.items():
+                if n not in adapter_sd or tuple(adapter_sd[n].shape) != s:
+                    raise KeyError(f"adapter_modules state_dict: missing/mis-shaped '{n}' (want {s}); keys are positional "
+                                   f"'{{i}}.to_q_lora.down.weight' in unet.attn_processors order")
         U = lambda n: unet_sd[n].to(device=device, dtype=dtype)
         A = lambda n: adapter_sd[n].to(device=device, dtype=dtype)
         put = self._put
         T = spec.time_embed_dim
         # stem / head
         put("conv_in.w", pack_conv3x3(U("conv_in.weight"), CIN_PAD)); put("conv_in.b", U("conv_in.bias"))
-        put("conv_out.w", pack_conv3x3(U("conv_out.weight"))); put("conv_out.b", U("conv_out.bias"))
-        put("norm_out.g", U("conv_norm_out.weight")); put("norm_out.b", U("conv_norm_out.bias"))
+        if is_unet:
+            put("conv_out.w", pack_conv3x3(U("conv_out.weight"))); put("conv_out.b", U("conv_out.bias"))
+            put("norm_out.g", U("conv_norm_out.weight")); put("norm_out.b", U("conv_norm_out.bias"))
         for k in ("time_embedding.linear_1", "time_embedding.linear_2"):
             put(k + ".w", U(k + ".weight")); put(k + ".b", U(k + ".bias"))
-        if spec.addition_embed_type == "text_time":
+        if spec.addition_embed_type == "text_time" and is_unet:
             w1 = U("add_embedding.linear_1.weight")
             n_text = w1.shape[1] - 6 * spec.addition_time_embed_dim
             put("add1.w_text", w1[:, :n_text].contiguous()); put("add1.w_time", w1[:, n_text:].contiguous())
@@ -63,6 +71,8 @@ class _Params:
         temb_w, temb_b, self.temb_off = [], [], {}
         off = 0
         for kind, i, layers, has_sampler in walk(spec):
+            if kind not in kinds:
+                continue
             for r, tf in layers:
                 n = r.name
                 put(n + ".n1.g", U(n + ".norm1.weight")); put(n + ".n1.b", U(n + ".norm1.bias"))
@@ -88,12 +98,15 @@ class _Params:
 
                     def folded(attn, pos, proj, out_name=None):
                         w = U(f"{b}.{attn}.{out_name or proj}.weight")
+                        if adapter_sd is None:
+                            return w
                         return fold_lora(w, A(f"{pos}.{proj}_lora.down.weight"), A(f"{pos}.{proj}_lora.up.weight"), lora_scale)
                     put(f"{b}.a1.qkv.w", torch.cat([folded("attn1", p1, "to_q"), folded("attn1", p1, "to_k"), folded("attn1", p1, "to_v")], 0))
                     put(f"{b}.a1.o.w", folded("attn1", p1, "to_out", "to_out.0")); put(f"{b}.a1.o.b", U(f"{b}.attn1.to_out.0.bias"))
                     put(f"{b}.a2.q.w", folded("attn2", p2, "to_q"))
                     put(f"{b}.a2.k.w", folded("attn2", p2, "to_k")); put(f"{b}.a2.v.w", folded("attn2", p2, "to_v"))
-                    put(f"{b}.a2.kip.w", A(f"{p2}.to_k_ip.weight")); put(f"{b}.a2.vip.w", A(f"{p2}.to_v_ip.weight"))
+                    if adapter_sd is not None:
+                        put(f"{b}.a2.kip.w", A(f"{p2}.to_k_ip.weight")); put(f"{b}.a2.vip.w", A(f"{p2}.to_v_ip.weight"))
                     put(f"{b}.a2.o.w", folded("attn2", p2, "to_out", "to_out.0")); put(f"{b}.a2.o.b", U(f"{b}.attn2.to_out.0.bias"))
                     w, bb = U(f"{b}.ff.net.0.proj.weight"), U(f"{b}.ff.net.0.proj.bias")
                     tile = lib.gemm_tile_n(w.shape[0], EPI_GEGLU)
@@ -107,7 +120,8 @@ class _Params:
                 put(nm + ".w", pack_conv3x3(U(nm + ".weight"))); put(nm + ".b", U(nm + ".bias"))
         put("temb_all.w", torch.cat(temb_w, 0)); put("temb_all.b", torch.cat(temb_b, 0))
         self.temb_total = off
-        self._finalize()
+        if finalize:
+            self._finalize()
 
     def _put(self, name, t):
         self._staged.append((name, t.contiguous()))
@@ -227,14 +241,16 @@ class B200UNet:
         L, cad = ehs.shape[1], ehs.shape[2]
         n_ip = self.num_tokens
         n_text = L - n_ip
-        if n_text > N_TEXT_MAX:
-            raise ValueError(f"{n_text} text tokens > {N_TEXT_MAX}")
+        if n_text > (N_TEXT_MAX if n_ip > 0 else KROWS):
+            raise ValueError(f"{n_text} text tokens do not fit the {KROWS}-row key tile")
         text = ehs[:, :n_text].reshape(NB * n_text, cad).contiguous()
-        ip = ehs[:, n_text:].reshape(NB * n_ip, cad).contiguous()
+        ip = ehs[:, n_text:].reshape(NB * n_ip, cad).contiguous() if n_ip > 0 else None
         P = self.params
         kv = {}
         tmp = lambda nm, rows, C: self._buf(nm, (rows, C))
         for kind, i, layers, _ in walk(self.spec):
+            if kind not in self.params.kinds:
+                continue
             for _, tf in layers:
                 if tf is None:
                     continue
@@ -242,9 +258,11 @@ class B200UNet:
                 for k in range(tf.layers):
                     b = f"{tf.name}.transformer_blocks.{k}"
                     kt, vt = tmp("kv_kt", NB * n_text, C), tmp("kv_vt", NB * n_text, C)
-                    ki, vi = tmp("kv_ki", NB * n_ip, C), tmp("kv_vi", NB * n_ip, C)
                     ops.gemm(text, P[f"{b}.a2.k.w"], kt); ops.gemm(text, P[f"{b}.a2.v.w"], vt)
-                    ops.gemm(ip, P[f"{b}.a2.kip.w"], ki); ops.gemm(ip, P[f"{b}.a2.vip.w"], vi)
+                    ki = vi = None
+                    if n_ip > 0:
+                        ki, vi = tmp("kv_ki", NB * n_ip, C), tmp("kv_vi", NB * n_ip, C)
+                        ops.gemm(ip, P[f"{b}.a2.kip.w"], ki); ops.gemm(ip, P[f"{b}.a2.vip.w"], vi)
                     k_cat = self._buf(f"kcat.{slot}.{b}", (NB, KROWS, C))
                     vt_cat = self._buf(f"vtcat.{slot}.{b}", (NB * Hh, C // Hh, KROWS))
                     ops.pack_cross_kv(kt, vt, ki, vi, k_cat, vt_cat, NB, C, Hh, n_text, n_ip)
@@ -267,20 +285,16 @@ class B200UNet:
         return key
 
     # ------------------------------------------------------------------ the per-step program
-    def forward(self, key=None, residuals=(None, None)):
-        """One UNet evaluation on the NHWC input already staged in buffer ``x_in`` (timestep in ``t_dev``); result rows
-        in buffer ``eps`` [NB*H*W, 4]."""
-        key = key if key is not None else self._active_key
-        NB, H, W = self._plan
+    # ------------------------------------------------------------------ building blocks of the launch program
+    def _time_embedding(self, key):
+        """SURVEY A.2 steps 1-2 -> (emb [NB,T], temb_all [NB, sum Cout]): all resnets' time_emb_proj in ONE skinny launch."""
+        NB = self._plan[0]
         spec, P, buf = self.spec, self.params, self._buf
-        G, T = spec.norm_num_groups, spec.time_embed_dim
-        kv = self._kv[key]
-        down_res, mid_res = residuals
-        # --- time embedding (SURVEY A.2 steps 1-2)
-        t_sin = buf("t_sin", (NB, spec.block_out_channels[0]))
-        ops.timestep_embed(buf("t_dev", (1,), torch.float32), 0, NB, spec.block_out_channels[0], t_sin, spec.block_out_channels[0])
+        T, c0 = spec.time_embed_dim, spec.block_out_channels[0]
+        t_sin = buf("t_sin", (NB, c0))
+        ops.timestep_embed(buf("t_dev", (1,), torch.float32), 0, NB, c0, t_sin, c0)
         e1 = buf("emb1", (NB, T))
-        ops.skinny_linear(t_sin, P["time_embedding.linear_1.w"], P["time_embedding.linear_1.b"], e1, NB, T, spec.block_out_channels[0])
+        ops.skinny_linear(t_sin, P["time_embedding.linear_1.w"], P["time_embedding.linear_1.b"], e1, NB, T, c0)
         emb = buf("emb", (NB, T))
         if spec.addition_embed_type == "text_time":
             emb.copy_(self._aug[key])
@@ -289,67 +303,102 @@ class B200UNet:
             ops.skinny_linear(e1, P["time_embedding.linear_2.w"], P["time_embedding.linear_2.b"], emb, NB, T, T, silu_in=True)
         temb_all = buf("temb_all", (NB, P.temb_total))
         ops.skinny_linear(emb, P["temb_all.w"], P["temb_all.b"], temb_all, NB, P.temb_total, T, silu_in=True)
+        return emb, temb_all
 
-        sums = buf("gn_sums", (NB, G, 2), torch.float32)
+    def _groupnorm(self, x1, C1, x2, C2, HW, g, b, eps, silu, out):
+        NB, G = self._plan[0], self.spec.norm_num_groups
+        sums = self._buf("gn_sums", (NB, G, 2), torch.float32)
+        ops.gn_stats(x1, C1, x2, C2, NB, HW, G, sums)
+        ops.gn_apply(x1, C1, x2, C2, NB, HW, G, sums, g, b, eps, silu, out)
 
-        def groupnorm(x1, C1, x2, C2, HW, g, b, eps, silu, out):
-            ops.gn_stats(x1, C1, x2, C2, NB, HW, G, sums)
-            ops.gn_apply(x1, C1, x2, C2, NB, HW, G, sums, g, b, eps, silu, out)
+    def _resnet(self, r, x, skip, h, w, out_name, temb_all):
+        """ResnetBlock2D on NHWC rows; ``skip`` = second source of the virtual channel concat (up path)."""
+        NB = self._plan[0]
+        spec, P, buf = self.spec, self.params, self._buf
+        HW = h * w
+        M = NB * HW
+        c_x = r.cin - r.skip_ch
+        act = buf("act", (M, r.cin))
+        self._groupnorm(x, c_x, skip, r.skip_ch, HW, P[r.name + ".n1.g"], P[r.name + ".n1.b"], spec.norm_eps, True, act)
+        h1 = buf("res_h1", (M, r.cout))
+        o = P.temb_off[r.name]
+        ops.conv3x3(act, P[r.name + ".c1.w"], h1, NB, h, w, r.cin, r.cout, bias=P[r.name + ".c1.b"], rowbias=temb_all[:, o:o + r.cout])
+        act2 = buf("act", (M, r.cout))
+        self._groupnorm(h1, r.cout, None, 0, HW, P[r.name + ".n2.g"], P[r.name + ".n2.b"], spec.norm_eps, True, act2)
+        if r.cin != r.cout:
+            res = buf("res_sc", (M, r.cout))
+            ops.gemm(x, P[r.name + ".sc.w"], res, bias=P[r.name + ".sc.b"], a2=skip)
+        else:
+            res = x
+        out = buf(out_name, (M, r.cout))
+        ops.conv3x3(act2, P[r.name + ".c2.w"], out, NB, h, w, r.cout, r.cout, bias=P[r.name + ".c2.b"], residual=res)
+        return out
 
-        def resnet(r, x, skip, h, w, out_name):
-            HW = h * w
-            M = NB * HW
-            c_x = r.cin - r.skip_ch
-            act = buf("act", (M, r.cin))
-            groupnorm(x, c_x, skip, r.skip_ch, HW, P[r.name + ".n1.g"], P[r.name + ".n1.b"], spec.norm_eps, True, act)
-            h1 = buf("res_h1", (M, r.cout))
-            o = P.temb_off[r.name]
-            ops.conv3x3(act, P[r.name + ".c1.w"], h1, NB, h, w, r.cin, r.cout, bias=P[r.name + ".c1.b"], rowbias=temb_all[:, o:o + r.cout])
-            act2 = buf("act", (M, r.cout))
-            groupnorm(h1, r.cout, None, 0, HW, P[r.name + ".n2.g"], P[r.name + ".n2.b"], spec.norm_eps, True, act2)
-            if r.cin != r.cout:
-                sc = buf("res_sc", (M, r.cout))
-                ops.gemm(x, P[r.name + ".sc.w"], sc, bias=P[r.name + ".sc.b"], a2=skip)
-                res = sc
-            else:
-                res = x
-            out = buf(out_name, (M, r.cout))
-            ops.conv3x3(act2, P[r.name + ".c2.w"], out, NB, h, w, r.cout, r.cout, bias=P[r.name + ".c2.b"], residual=res)
-            return out
+    def _transformer(self, tf, x, h, w, out_name, kv):
+        """Transformer2DModel: GN -> proj_in -> [LN, self-attn, LN, decoupled cross-attn, LN, GEGLU FF] x layers -> proj_out + x."""
+        NB = self._plan[0]
+        P, buf = self.params, self._buf
+        HW = h * w
+        M = NB * HW
+        C, Hh = tf.channels, tf.heads
+        d = C // Hh
+        gn = buf("act", (M, C))
+        self._groupnorm(x, C, None, 0, HW, P[tf.name + ".norm.g"], P[tf.name + ".norm.b"], 1e-6, False, gn)
+        t = buf("tf_h", (M, C))
+        ops.gemm(gn, P[tf.name + ".pi.w"], t, bias=P[tf.name + ".pi.b"])
+        ln, qk = buf("tf_ln", (M, C)), buf("tf_qk", (M, 2 * C))
+        vt, ao = buf("tf_vt", (NB * Hh, d, HW)), buf("tf_ao", (M, C))
+        q, ffm = buf("tf_q", (M, C)), buf("tf_ffm", (M, 4 * C))
+        for k in range(tf.layers):
+            b = f"{tf.name}.transformer_blocks.{k}"
+            ops.layernorm(t, P[b + ".ln1.g"], P[b + ".ln1.b"], ln, M, C)
+            ops.gemm(ln, P[b + ".a1.qkv.w"], qk, epi=EPI_QKV, vt=vt, n_split=2 * C, heads=Hh, hdim=d, ntok=HW)
+            ops.attn_self(qk[:, :C], qk[:, C:], vt, ao, NB, Hh, HW, d)
+            ops.gemm(ao, P[b + ".a1.o.w"], t, bias=P[b + ".a1.o.b"], residual=t)
+            ops.layernorm(t, P[b + ".ln2.g"], P[b + ".ln2.b"], ln, M, C)
+            ops.gemm(ln, P[b + ".a2.q.w"], q)
+            k_cat, vt_cat, n_text, n_ip = kv[b]
+            ops.attn_cross(q, k_cat, vt_cat, ao, NB, Hh, HW, d, n_text, n_ip, self.ip_scale)
+            ops.gemm(ao, P[b + ".a2.o.w"], t, bias=P[b + ".a2.o.b"], residual=t)
+            ops.layernorm(t, P[b + ".ln3.g"], P[b + ".ln3.b"], ln, M, C)
+            ops.gemm(ln, P[b + ".ff1.w"], ffm, bias=P[b + ".ff1.b"], epi=EPI_GEGLU)
+            ops.gemm(ffm, P[b + ".ff2.w"], t, bias=P[b + ".ff2.b"], residual=t)
+        out = buf(out_name, (M, C))
+        ops.gemm(t, P[tf.name + ".po.w"], out, bias=P[tf.name + ".po.b"], residual=x)
+        return out
 
-        def transformer(tf, x, h, w, out_name):
-            HW = h * w
-            M = NB * HW
-            C, Hh = tf.channels, tf.heads
-            d = C // Hh
-            gn = buf("act", (M, C))
-            groupnorm(x, C, None, 0, HW, P[tf.name + ".norm.g"], P[tf.name + ".norm.b"], 1e-6, False, gn)
-            t = buf("tf_h", (M, C))
-            ops.gemm(gn, P[tf.name + ".pi.w"], t, bias=P[tf.name + ".pi.b"])
-            ln = buf("tf_ln", (M, C))
-            qk = buf("tf_qk", (M, 2 * C))
-            vt = buf("tf_vt", (NB * Hh, d, HW))
-            ao = buf("tf_ao", (M, C))
-            q = buf("tf_q", (M, C))
-            ffm = buf("tf_ffm", (M, 4 * C))
-            for k in range(tf.layers):
-                b = f"{tf.name}.transformer_blocks.{k}"
-                ops.layernorm(t, P[b + ".ln1.g"], P[b + ".ln1.b"], ln, M, C)
-                ops.gemm(ln, P[b + ".a1.qkv.w"], qk, epi=EPI_QKV, vt=vt, n_split=2 * C, heads=Hh, hdim=d, ntok=HW)
-                ops.attn_self(qk[:, :C], qk[:, C:], vt, ao, NB, Hh, HW, d)
-                ops.gemm(ao, P[b + ".a1.o.w"], t, bias=P[b + ".a1.o.b"], residual=t)
-                ops.layernorm(t, P[b + ".ln2.g"], P[b + ".ln2.b"], ln, M, C)
-                ops.gemm(ln, P[b + ".a2.q.w"], q)
-                k_cat, vt_cat, n_text, n_ip = kv[b]
-                ops.attn_cross(q, k_cat, vt_cat, ao, NB, Hh, HW, d, n_text, n_ip, self.ip_scale)
-                ops.gemm(ao, P[b + ".a2.o.w"], t, bias=P[b + ".a2.o.b"], residual=t)
-                ops.layernorm(t, P[b + ".ln3.g"], P[b + ".ln3.b"], ln, M, C)
-                ops.gemm(ln, P[b + ".ff1.w"], ffm, bias=P[b + ".ff1.b"], epi=EPI_GEGLU)
-                ops.gemm(ffm, P[b + ".ff2.w"], t, bias=P[b + ".ff2.b"], residual=t)
-            out = buf(out_name, (M, C))
-            ops.gemm(t, P[tf.name + ".po.w"], out, bias=P[tf.name + ".po.b"], residual=x)
-            return out
+    def _downsample(self, x, i, h, w, c):
+        NB, P, buf = self._plan[0], self.params, self._buf
+        ps = buf("phase", (NB * h * w, c))
+        ops.phase_split(x, ps, NB, h, w, c)
+        nm = f"down_blocks.{i}.downsamplers.0.conv"
+        out = buf(f"h.{nm}", (NB * (h // 2) * (w // 2), c))
+        ops.conv3x3(ps, P[nm + ".w"], out, NB, h // 2, w // 2, c, c, bias=P[nm + ".b"], stride2=True)
+        return out
 
+    def _add_residual(self, dst, res, c):
+        """dst[M, c] += ControlNet residual.  ``res`` is NCHW (drop-in API) or NHWC rows; a residual computed for B samples is
+        applied to both CFG halves of a 2B batch (the reference broadcasts [1,...] onto [2,...],
+        pipelines/StableDIffusionControlNetInpaint_ConsistentID.py:389-425)."""
+        rows = res if res.ndim == 2 else self._to_rows(res, c)
+        M = dst.shape[0]
+        if rows.shape[0] == M:
+            ops.add_inplace(dst, rows)
+        else:
+            assert rows.shape[0] * 2 == M, (rows.shape, dst.shape)
+            ops.add_inplace(dst[:M // 2], rows)
+            ops.add_inplace(dst[M // 2:], rows)
+
+    # ------------------------------------------------------------------ the per-step program
+    def forward(self, key=None, residuals=(None, None)):
+        """One UNet evaluation on the NHWC input already staged in buffer ``x_in`` (timestep in ``t_dev``); result rows
+        in buffer ``eps`` [NB*H*W, 4]."""
+        key = key if key is not None else self._active_key
+        NB, H, W = self._plan
+        spec, P, buf = self.spec, self.params, self._buf
+        kv = self._kv[key]
+        down_res, mid_res = residuals
+        emb, temb_all = self._time_embedding(key)
         # --- stem
         h, w = H, W
         c0 = spec.block_out_channels[0]
@@ -363,29 +412,27 @@ class B200UNet:
                 for idx, ((sk, c), r_) in enumerate(zip(list(skips), down_res)):
                     cp = buf(f"skipres.{idx}", tuple(sk.shape))
                     cp.copy_(sk)
-                    ops.add_inplace(cp, self._to_rows(r_, c))
+                    self._add_residual(cp, r_, c)
                     skips[idx] = (cp, c)
             for j, (r, tf) in enumerate(layers):
                 skip = None
                 if kind == "up":
                     skip, _ = skips.pop()
-                x = resnet(r, x, skip, h, w, f"h.{r.name}")
+                x = self._resnet(r, x, skip, h, w, f"h.{r.name}", temb_all)
                 if tf is not None:
-                    x = transformer(tf, x, h, w, f"h.{tf.name}")
+                    x = self._transformer(tf, x, h, w, f"h.{tf.name}", kv)
                 if kind == "down":
                     skips.append((x, r.cout))
             if kind == "mid" and mid_res is not None:
-                ops.add_inplace(x, self._to_rows(mid_res, layers[-1][0].cout))
+                xm = buf("midres", tuple(x.shape))
+                xm.copy_(x)
+                self._add_residual(xm, mid_res, layers[-1][0].cout)
+                x = xm
             if has_sampler:
                 c = layers[-1][0].cout
                 if kind == "down":
-                    ps = buf("phase", (NB * h * w, c))
-                    ops.phase_split(x, ps, NB, h, w, c)
+                    x = self._downsample(x, i, h, w, c)
                     h, w = h // 2, w // 2
-                    nm = f"down_blocks.{i}.downsamplers.0.conv"
-                    x2 = buf(f"h.{nm}", (NB * h * w, c))
-                    ops.conv3x3(ps, P[nm + ".w"], x2, NB, h, w, c, c, bias=P[nm + ".b"], stride2=True)
-                    x = x2
                     skips.append((x, c))
                 else:
                     up = buf("upsampled", (NB * 4 * h * w, c))
@@ -397,7 +444,7 @@ class B200UNet:
                     x = x2
         # --- head
         act = buf("act", (NB * h * w, c0))
-        groupnorm(x, c0, None, 0, h * w, P["norm_out.g"], P["norm_out.b"], spec.norm_eps, True, act)
+        self._groupnorm(x, c0, None, 0, h * w, P["norm_out.g"], P["norm_out.b"], spec.norm_eps, True, act)
         eps = buf("eps", (NB * H * W, 4))
         ops.conv3x3(act, P["conv_out.w"], eps, NB, h, w, c0, spec.out_channels, bias=P["conv_out.b"])
         return eps

@@ -84,7 +84,16 @@ int cid_cfg_sched_step(const void* eps, int ld_eps, float* x, float* x0_prev, vo
                        int HW, float guidance, const float* coef_table, const int* step_dev, int dtype, void* stream);
 /* in-graph step bookkeeping: *step_dev += 1; *t_dev = ts_table[min(*step_dev, n-1)] */
 int cid_advance_step(int* step_dev, float* t_dev, const float* ts_table, int n, void* stream);
-int cid_latents_to_input(const float* x, void* next_in, int CP, int B, int HW, const float* coef_table, int dtype, void* stream);
+/* fp32 master latents -> scaled, batch-duplicated NHWC UNet input for the step *step_dev (NULL = step 0);
+ * keep_ch4_up = 1 writes channels 0-3 only (9-channel inpaint UNet keeps mask / masked-latent channels). */
+int cid_latents_to_input(const float* x, void* next_in, int CP, int B, int HW, const float* coef_table, const int* step_dev, int nsteps,
+                         int keep_ch4_up, int dtype, void* stream);
+/* y = silu(y) */
+int cid_silu_inplace(void* y, long long n_elems, int dtype, void* stream);
+/* inpaint blend after a scheduler step (pipelines/StableDIffusionControlNetInpaint_ConsistentID.py:437-449):
+ * x = (1-m) * (ca*image_latents + cn*noise) + m*x with {ca,cn} = blend_table[*step_dev] */
+int cid_inpaint_blend(float* x, void* x16, const float* image_latents, const float* noise, const float* mask, int B, int HW,
+                      const float* blend_table, const int* step_dev, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -60,3 +60,38 @@ def denoise_sdxl(unet, scheduler, latents, neg_text_only, pos_text_only, neg_fac
         if callback is not None:
             callback(i, t, latents)
     return latents
+
+
+@torch.no_grad()
+def denoise_controlnet_inpaint(unet, controlnet, scheduler, latents, null_embeds, augmented_embeds, text_embeds, control_image,
+                               image_latents, noise, mask, num_inference_steps, guidance_scale=5.0, start_merge_step=0,
+                               conditioning_scale=1.0, masked_image_latents=None):
+    """pipelines/StableDIffusionControlNetInpaint_ConsistentID.py:375-449 (strength 1.0): ControlNet on the cond half only,
+    its residuals added to BOTH CFG halves of the UNet (the reference broadcasts batch 1 onto batch 2), CFG, scheduler step and,
+    for the 4-channel UNet, the latent blend with the re-noised original.  ``mask`` [B,1,h,w]: 1 = repaint.
+    9-channel UNet: pass ``masked_image_latents`` [B,4,h,w] (concatenated with the mask every step, :414-415)."""
+    b = latents.shape[0]
+    scheduler.set_timesteps(num_inference_steps, device=latents.device)
+    ts = scheduler.timesteps
+    for i, t in enumerate(ts):
+        x_in = scheduler.scale_model_input(torch.cat([latents] * 2), t)
+        cond = text_embeds if i <= start_merge_step else augmented_embeds
+        ehs = torch.cat([null_embeds.expand(b, -1, -1), cond.expand(b, -1, -1)], dim=0)
+        c_in = scheduler.scale_model_input(latents, t)
+        down, mid = controlnet(c_in, t, encoder_hidden_states=cond.expand(b, -1, -1), controlnet_cond=control_image,
+                               conditioning_scale=conditioning_scale)
+        down2 = [torch.cat([d, d]) for d in down]
+        mid2 = torch.cat([mid, mid])
+        if masked_image_latents is not None:
+            x_in = torch.cat([x_in, torch.cat([mask] * 2), torch.cat([masked_image_latents] * 2)], dim=1)
+        eps = unet(x_in, t, encoder_hidden_states=ehs, cross_attention_kwargs={}, down_block_additional_residuals=down2,
+                   mid_block_additional_residual=mid2).sample
+        eps_u, eps_c = eps.chunk(2)
+        eps = eps_u + guidance_scale * (eps_c - eps_u)
+        latents = scheduler.step(eps, t, latents).prev_sample
+        if masked_image_latents is None:
+            proper = image_latents
+            if i < len(ts) - 1:
+                proper = scheduler.add_noise(image_latents, noise, torch.tensor([int(ts[i + 1])]))
+            latents = (1 - mask) * proper + mask * latents
+    return latents
