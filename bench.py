@@ -32,6 +32,9 @@ WORKLOADS = {
     # BASELINE.json configs[2]: SDXL ConsistentID 1024x1024 batch=4, 30 steps, bf16, 1xB200
     "sdxl": dict(model="sdxl", res=1024, batch=4, denoise_steps=30, dtype="bf16", scheduler="euler", guidance=7.5, start_merge_step=0,
                  tflop_per_sample_forward=6.7657),
+    # BASELINE.json configs[4]: SD1.5 ControlNet+Inpaint ConsistentID 512x512 batch=8, 50 steps, dual-network path (blend variant, 4-ch UNet)
+    "sd15_cn": dict(model="sd15", res=512, batch=8, denoise_steps=50, dtype="fp16", scheduler="ddim", guidance=5.0, start_merge_step=0,
+                    tflop_per_sample_forward=0.8036, controlnet=True, controlnet_tflop_per_image_step=0.283),
     # reduced-width variants for quick functional runs (NOT a bench result)
     "tiny": dict(model="tiny_sd15", res=256, batch=2, denoise_steps=4, dtype="fp16", scheduler="ddim", guidance=5.0, start_merge_step=0,
                  tflop_per_sample_forward=None),
@@ -145,6 +148,13 @@ def run_ours(args):
         if rank != 0:
             unet.params.arena.zero_()
         cdist.broadcast_arena(unet.params.arena, src=0)
+        # every rank must now hold rank 0's bytes: compare an integer checksum of the arena across ranks
+        chk = unet.params.arena.view(torch.int16).to(torch.int64).sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN); torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+        weights_identical = bool((lo == hi).item())
+    else:
+        weights_identical = True
     torch.cuda.synchronize()
     t_build = time.time() - t0
 
@@ -159,17 +169,58 @@ def run_ours(args):
     out_h = torch.empty((B, 4, h, h), dtype=dtype).pin_memory()
     kw = dict(num_inference_steps=n_steps, guidance_scale=wl["guidance"], start_merge_step=wl["start_merge_step"])
 
+    use_cn = bool(wl.get("controlnet"))
+    if use_cn:
+        from consistentid_b200.arch import param_shapes
+        from consistentid_b200.controlnet import B200ControlNet
+        import torch.nn.functional as F
+        gcn = torch.Generator(device=dev).manual_seed(4321)
+        ush, _ = param_shapes(spec, rankN)
+        cn_sd = {k: v for k, v in synth_state_dicts(spec, dev, dtype, seed=99, rank=rankN)[0].items()
+                 if k.startswith(("conv_in", "time_embedding", "down_blocks", "mid_block"))}
+        def rw(*shape):
+            fan = 1
+            for x_ in shape[1:]:
+                fan *= x_
+            return (torch.randn(shape, generator=gcn, device=dev) * fan ** -0.5).to(dtype)
+        ch = (16, 32, 96, 256)
+        cn_sd["controlnet_cond_embedding.conv_in.weight"], cn_sd["controlnet_cond_embedding.conv_in.bias"] = rw(ch[0], 3, 3, 3), rw(ch[0])
+        for i in range(3):
+            cn_sd[f"controlnet_cond_embedding.blocks.{2*i}.weight"], cn_sd[f"controlnet_cond_embedding.blocks.{2*i}.bias"] = rw(ch[i], ch[i], 3, 3), rw(ch[i])
+            cn_sd[f"controlnet_cond_embedding.blocks.{2*i+1}.weight"], cn_sd[f"controlnet_cond_embedding.blocks.{2*i+1}.bias"] = rw(ch[i + 1], ch[i], 3, 3), rw(ch[i + 1])
+        c0 = spec.block_out_channels[0]
+        cn_sd["controlnet_cond_embedding.conv_out.weight"], cn_sd["controlnet_cond_embedding.conv_out.bias"] = rw(c0, ch[3], 3, 3), rw(c0)
+        zc = [c0] + [c for i, c in enumerate(spec.block_out_channels) for _ in range(spec.layers_per_block + (0 if i == len(spec.block_out_channels) - 1 else 1))]
+        for j, c in enumerate(zc):
+            cn_sd[f"controlnet_down_blocks.{j}.weight"], cn_sd[f"controlnet_down_blocks.{j}.bias"] = rw(c, c, 1, 1), rw(c)
+        cn_sd["controlnet_mid_block.weight"], cn_sd["controlnet_mid_block.bias"] = rw(zc[-1], zc[-1], 1, 1), rw(zc[-1])
+        cnet = B200ControlNet(spec, cn_sd, dtype=dtype, device=dev)
+        del cn_sd
+        gh = torch.Generator().manual_seed(7)
+        ctrl_h = torch.rand(B, 3, wl["res"], wl["res"], generator=gh).to(dtype).pin_memory()
+        img_h = torch.randn(B, 4, h, h, generator=gh).pin_memory(); noise_h = torch.randn(B, 4, h, h, generator=gh).pin_memory()
+        mask_h = torch.zeros(B, 1, h, h); mask_h[:, :, h // 4: 3 * h // 4, h // 4: 3 * h // 4] = 1; mask_h = mask_h.pin_memory()
+
     def job_resident(lat_d, prompts_d, extra_d):
+        if use_cn:
+            return den.controlnet_inpaint(cnet, lat_d, prompts_d[0], prompts_d[1], prompts_d[2], ctrl_d, img_d, noise_d, mask_d,
+                                          conditioning_scale=0.5, **kw)
         return den(lat_d, prompts_d[0], prompts_d[1], prompts_d[2], **kw, **extra_d)
 
     def job_e2e():
         lat_d = lat_h.to(dev, non_blocking=True)
         pd = [p.to(dev, non_blocking=True) for p in prompts_h]
         ed = {k: v.to(dev, non_blocking=True) for k, v in extra_h.items()}
-        out = den(lat_d, pd[0], pd[1], pd[2], **kw, **ed)
+        if use_cn:
+            out = den.controlnet_inpaint(cnet, lat_d, pd[0], pd[1], pd[2], ctrl_h.to(dev, non_blocking=True), img_h.to(dev, non_blocking=True),
+                                         noise_h.to(dev, non_blocking=True), mask_h.to(dev, non_blocking=True), conditioning_scale=0.5, **kw)
+        else:
+            out = den(lat_d, pd[0], pd[1], pd[2], **kw, **ed)
         out_h.copy_(out, non_blocking=True)
 
     lat_d = lat_h.to(dev); prompts_d = [p.to(dev) for p in prompts_h]; extra_d = {k: v.to(dev) for k, v in extra_h.items()}
+    if use_cn:
+        ctrl_d, img_d, noise_d, mask_d = ctrl_h.to(dev), img_h.to(dev), noise_h.to(dev), mask_h.to(dev)
     # ---- warm-up (also captures the CUDA graphs)
     for _ in range(max(args.warmup, 1)):
         job_resident(lat_d, prompts_d, extra_d)
@@ -197,7 +248,7 @@ def run_ours(args):
 
     # ---- launches: kernels inside the captured per-step graphs x replays + eager launches
     per_step = None
-    if den.use_cuda_graph:
+    if den.use_cuda_graph and not use_cn:
         c0 = lib.LAUNCHES
         den_e = B200Denoiser(unet, sched, use_cuda_graph=False)
         den_e(lat_d, prompts_d[0], prompts_d[1], prompts_d[2], **dict(kw, num_inference_steps=n_steps), **extra_d)
@@ -221,18 +272,20 @@ def run_ours(args):
                    "cuda_graph": den.use_cuda_graph, "l2_policy": "working set >> L2: weights + per-step activations exceed 126 MB, no flush needed"},
         "clocks": clk,
         "e2e": {"value": round(e2e_img_per_s, 4), "unit": "images/s",
-                "h2d_bytes_per_step": int(lat_h.numel() * 2 + sum(p.numel() * 2 for p in prompts_h) + sum(v.numel() * v.element_size() for v in extra_h.values())),
+                "h2d_bytes_per_step": int(lat_h.numel() * 2 + sum(p.numel() * 2 for p in prompts_h) + sum(v.numel() * v.element_size() for v in extra_h.values())
+                                          + ((ctrl_h.numel() * 2 + (img_h.numel() + noise_h.numel() + mask_h.numel()) * 4) if use_cn else 0)),
                 "d2h_bytes_per_step": int(out_h.numel() * 2), "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": int(gpu_launches), "launches_per_denoise_step": per_step, "finite_output": finite,
+        "weights_identical_after_broadcast": weights_identical,
         "build_s": round(t_build, 1),
     }
     if wl["tflop_per_sample_forward"]:
-        tf_job = wl["tflop_per_sample_forward"] * 2 * B * n_steps
+        tf_job = (wl["tflop_per_sample_forward"] * 2 + wl.get("controlnet_tflop_per_image_step", 0.0)) * B * n_steps
         res["step_tflops"] = {"algorithmic_tflop_per_step": round(tf_job, 2), "achieved_tflops_per_gpu": round(tf_job / (ms_total / args.steps / 1e3), 1),
                               "frac_of_sustained_peak": round(tf_job / (ms_total / args.steps / 1e3) / pk["tf_sustained"], 4), "peak_src": pk["src"]}
 
     # ---- roofline of the dominant kernel: every tensor-core launch of ONE eager denoising step bracketed by CUDA events
-    if rank == 0 and not args.no_profile:
+    if rank == 0 and not args.no_profile and not use_cn:
         try:
             den_p = B200Denoiser(unet, sched, use_cuda_graph=False)
             den_p(lat_d, prompts_d[0], prompts_d[1], prompts_d[2], **dict(kw, num_inference_steps=2, start_merge_step=-1), **extra_d)  # warm
