@@ -322,6 +322,9 @@ def run_ours(args):
             res["cpu_baseline"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(res), flush=True)
+    if world > 1:
+        cdist.barrier()
+        torch.distributed.destroy_process_group()
 
 
 def cpu_baseline(workload, steps=1, warmup=0):
