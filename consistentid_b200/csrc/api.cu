@@ -17,6 +17,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "gemm_tc3.cuh"
+#include "gemm_tc4.cuh"
 
 using namespace cid;
 
@@ -102,12 +103,13 @@ int num_sms() {
   return g_num_sms;
 }
 // 1 = one-tile-per-CTA kernel (gemm_tc.cuh), 2 = persistent 1-CTA kernel (gemm_tc2.cuh, default),
-// 3 = persistent 2-CTA pairs (gemm_tc3.cuh; parity-green, measured no faster than 2 on B200 - see DESIGN.md)
+// 3 = persistent 2-CTA pairs (gemm_tc3.cuh; parity-green, measured no faster than 2 on B200 - see DESIGN.md),
+// 4 = version 2 with two k-blocks per TMA instruction for the 160/64-wide tiles (gemm_tc4.cuh, default)
 int g_gemm_version = 0;
 int gemm_version() {
   if (g_gemm_version == 0) {
     const char* e = getenv("CID_GEMM_VERSION");
-    g_gemm_version = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 2;
+    g_gemm_version = (e && e[0] >= '1' && e[0] <= '4') ? (e[0] - '0') : 4;
   }
   return g_gemm_version;
 }
@@ -149,6 +151,35 @@ int launch_gemm3(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap
 // rows of B staged per CTA (= TMA box height of the weight map)
 int b_box_rows(int bn) { return (gemm_version() == 3 && bn >= 32) ? bn / 2 : bn; }
 
+template <int BN, int STAGES, int KPI>
+int launch_gemm4(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
+  using SM = Gemm4Smem<BN, STAGES, KPI>;
+  static bool configured = false;
+  if (!configured) {
+    int rc = set_smem(gemm_tc4_kernel<BN, STAGES, KPI>, SM::TOTAL, "gemm_tc4_kernel");
+    if (rc) return rc;
+    configured = true;
+  }
+  const int n_tiles = (g.N + BN - 1) / BN;
+  const int total = n_tiles * m_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_tc4_kernel<BN, STAGES, KPI><<<grid, GEMM2_THREADS, SM::TOTAL, st>>>(a1, a2, b, g, n_tiles, total);
+  CID_CHECK_LAUNCH("gemm_tc4_kernel");
+  return 0;
+}
+// [rows, K] operand viewed as {64, rows, K/64}: box {64, box_rows, 2} = two k-blocks per TMA instruction
+int map_3d_k(CUtensorMap* m, const void* base, long long K, long long rows, long long pitch_elems, int box_rows) {
+  cuuint64_t dims[3] = {64, cuuint64_t(rows), cuuint64_t(K / 64)};
+  cuuint64_t str[2] = {cuuint64_t(pitch_elems) * 2, 128};
+  cuuint32_t box[3] = {64, cuuint32_t(box_rows), 2};
+  return make_map(m, base, 3, dims, str, box);
+}
+bool use_v4(int bn) { return gemm_version() == 4 && (bn == 160 || bn == 64); }
+int dispatch_gemm4(int bn, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
+  if (bn == 160) return launch_gemm4<160, 3, 2>(a1, a2, b, g, m_tiles, st);
+  return launch_gemm4<64, 4, 2>(a1, a2, b, g, m_tiles, st);
+}
+
 int dispatch_gemm(int bn, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
   if (gemm_version() == 3 && bn >= 32) {
     switch (bn) {
@@ -158,7 +189,7 @@ int dispatch_gemm(int bn, const CUtensorMap& a1, const CUtensorMap& a2, const CU
     }
     return fail(CID_ERR_UNSUPPORTED, "no 2-CTA GEMM instantiation for tile N %d", bn);
   }
-  if (gemm_version() >= 2) {
+  if (gemm_version() >= 2) {      // (version 4 falls through to the 1-CTA kernel for tiles it does not cover)
     switch (bn) {
       case 256: return launch_gemm2<256, 4>(a1, a2, b, g, m_tiles, st);
       case 160: return launch_gemm2<160, 5>(a1, a2, b, g, m_tiles, st);
@@ -282,15 +313,23 @@ int cid_gemm(const void* A, long long lda, const void* A2, long long lda2, int K
     return fail(CID_ERR_ARG, "cid_gemm: bad QKV epilogue arguments");
   CUtensorMap ta1, ta2, tb;
   int rc;
-  if ((rc = map_2d(&ta1, A, K1, M, lda, 128))) return rc;
-  if (K2 > 0) { if ((rc = map_2d(&ta2, A2, K2, M, lda2, 128))) return rc; } else ta2 = ta1;
-  if ((rc = map_2d(&tb, B, K1 + K2, N, K1 + K2, b_box_rows(bn)))) return rc;
+  const bool v4 = use_v4(bn);
+  if (v4) {
+    if ((rc = map_3d_k(&ta1, A, K1, M, lda, 128))) return rc;
+    if (K2 > 0) { if ((rc = map_3d_k(&ta2, A2, K2, M, lda2, 128))) return rc; } else ta2 = ta1;
+    if ((rc = map_3d_k(&tb, B, K1 + K2, N, K1 + K2, bn))) return rc;
+  } else {
+    if ((rc = map_2d(&ta1, A, K1, M, lda, 128))) return rc;
+    if (K2 > 0) { if ((rc = map_2d(&ta2, A2, K2, M, lda2, 128))) return rc; } else ta2 = ta1;
+    if ((rc = map_2d(&tb, B, K1 + K2, N, K1 + K2, b_box_rows(bn)))) return rc;
+  }
   GemmArgs g{};
   g.M = M; g.N = N; g.kblocks_a1 = K1 / 64; g.kblocks_a2 = K2 / 64; g.taps = 1; g.a_mode = A_GEMM;
   g.C = C; g.ldc = ldc; g.bias = bias; g.residual = residual; g.ldr = ldr;
   g.rowbias = rowbias; g.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; g.ld_rowbias = ld_rowbias;
   g.epi = epi; g.is_bf16 = dtype == CID_BF16; g.Vt = Vt; g.n_split = n_split; g.heads = heads; g.hdim = hdim; g.ntok = ntok;
   g.out_scale = out_scale;
+  if (v4) return dispatch_gemm4(bn, ta1, ta2, tb, g, (M + 127) / 128, static_cast<cudaStream_t>(stream));
   return dispatch_gemm(bn, ta1, ta2, tb, g, (M + 127) / 128, static_cast<cudaStream_t>(stream));
 }
 
@@ -313,7 +352,13 @@ int cid_conv3x3(const void* X, const void* Wt, void* Y, long long ldy, int NB, i
   const int bn = cid_gemm_tile_n(Cout, CID_EPI_STORE);
   CUtensorMap ta, tb;
   int rc;
-  if (!stride2) {
+  const bool v4 = use_v4(bn) && !stride2 && ((g.TW * g.TH * g.TN) % 8 == 0);
+  if (v4) {
+    cuuint64_t dims[5] = {64, cuuint64_t(W), cuuint64_t(H), cuuint64_t(NB), cuuint64_t(Cin / 64)};
+    cuuint64_t str[4] = {cuuint64_t(Cin) * 2, cuuint64_t(W) * Cin * 2, cuuint64_t(H) * W * Cin * 2, 128};
+    cuuint32_t box[5] = {64, cuuint32_t(g.TW), cuuint32_t(g.TH), cuuint32_t(g.TN), 2};
+    if ((rc = make_map(&ta, X, 5, dims, str, box))) return rc;
+  } else if (!stride2) {
     cuuint64_t dims[4] = {cuuint64_t(Cin), cuuint64_t(W), cuuint64_t(H), cuuint64_t(NB)};
     cuuint64_t str[3] = {cuuint64_t(Cin) * 2, cuuint64_t(W) * Cin * 2, cuuint64_t(H) * W * Cin * 2};
     cuuint32_t box[4] = {64, cuuint32_t(g.TW), cuuint32_t(g.TH), cuuint32_t(g.TN)};
@@ -324,12 +369,14 @@ int cid_conv3x3(const void* X, const void* Wt, void* Y, long long ldy, int NB, i
     cuuint32_t box[5] = {64, cuuint32_t(g.TW), cuuint32_t(g.TH), 1, cuuint32_t(g.TN)};
     if ((rc = make_map(&ta, X, 5, dims, str, box))) return rc;
   }
-  if ((rc = map_2d(&tb, Wt, 9LL * Cin, Cout, 9LL * Cin, b_box_rows(bn)))) return rc;
+  if (v4) { if ((rc = map_3d_k(&tb, Wt, 9LL * Cin, Cout, 9LL * Cin, bn))) return rc; }
+  else if ((rc = map_2d(&tb, Wt, 9LL * Cin, Cout, 9LL * Cin, b_box_rows(bn)))) return rc;
   g.M = NB * H * W; g.N = Cout; g.kblocks_a1 = Cin / 64; g.kblocks_a2 = 0; g.taps = 9;
   g.a_mode = stride2 ? A_CONV_S2 : A_CONV; g.W = W; g.H = H; g.NB = NB;
   g.C = Y; g.ldc = ldy; g.bias = bias; g.residual = residual; g.ldr = ldr;
   g.rowbias = rowbias; g.rows_per_group = H * W; g.ld_rowbias = ld_rowbias;
   g.epi = EPI_STORE; g.is_bf16 = dtype == CID_BF16; g.out_scale = out_scale;
+  if (v4) return dispatch_gemm4(bn, ta, ta, tb, g, m_tiles, static_cast<cudaStream_t>(stream));
   return dispatch_gemm(bn, ta, ta, tb, g, m_tiles, static_cast<cudaStream_t>(stream));
 }
 

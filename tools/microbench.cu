@@ -13,10 +13,10 @@
 #include "common.cuh"
 using namespace cid;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int KPI>
 __global__ void __launch_bounds__(128, 1) mb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                      int mode, int nkb, int k_blocks_total, long long* out_cycles) {
-  constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE = A_BYTES + B_BYTES;
+  constexpr int A_BYTES = 128 * 128 * KPI, B_BYTES = BN * 128 * KPI, STAGE = A_BYTES + B_BYTES;   // a stage holds KPI k-blocks
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar = base + STAGES * STAGE;
@@ -40,9 +40,9 @@ __global__ void __launch_bounds__(128, 1) mb_kernel(const __grid_constant__ CUte
       if (mode == 3) mbar_wait(empty(stage), phase ^ 1u);
       else if (kb >= STAGES) mbar_wait(full(stage), phase ^ 1u);      // previous load into this stage landed
       mbar_expect_tx(full(stage), STAGE);
-      const int kcol = (kb % k_blocks_total) * 64;
-      tma_load_2d(base + stage * STAGE, &tmA, full(stage), kcol, m_row);
-      tma_load_2d(base + stage * STAGE + A_BYTES, &tmB, full(stage), kcol, 0);
+      const int kchunk = (kb * KPI) % k_blocks_total;
+      tma_load_3d(base + stage * STAGE, &tmA, full(stage), 0, m_row, kchunk);             // box {64, 128, KPI}
+      tma_load_3d(base + stage * STAGE + A_BYTES, &tmB, full(stage), 0, 0, kchunk);       // box {64, BN, KPI}
       if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     }
     // drain
@@ -59,13 +59,17 @@ __global__ void __launch_bounds__(128, 1) mb_kernel(const __grid_constant__ CUte
       if (mode == 3) { mbar_wait(full(stage), phase); tc_fence_after(); }
       const uint32_t a_lo = a0 + stage * (STAGE / 16), b_lo = a_lo + A_BYTES / 16;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_ss(tmem, desc_make(a_lo + k * 2), desc_make(b_lo + k * 2), idesc, (kb | k) ? 1u : 0u);
+      for (int q = 0; q < KPI; ++q)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(tmem, desc_make(a_lo + q * 1024 + k * 2), desc_make(b_lo + q * (BN * 8) + k * 2), idesc, (kb | k | q) ? 1u : 0u);
       if (mode == 3) umma_commit(empty(stage));
       if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     }
     umma_commit(done);
     mbar_wait(done, 0);
   }
+  __syncwarp();                                            // reconverge before the block barrier (diverged bar.sync is UB)
   __syncthreads();
   const long long t1 = clock64();
   if (threadIdx.x == 0) out_cycles[blockIdx.x] = t1 - t0;
@@ -73,26 +77,28 @@ __global__ void __launch_bounds__(128, 1) mb_kernel(const __grid_constant__ CUte
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 enc;
-static void map2d(CUtensorMap* m, void* p, long long inner, long long rows, int box_rows) {
-  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows}; cuuint64_t str[1] = {(cuuint64_t)inner * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows}, es[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, p, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+static void map3d(CUtensorMap* m, void* p, long long K, long long rows, int box_rows, int kpi) {
+  // view [rows, K] as {64 (contiguous), rows (pitch K), K/64 chunks (pitch 64)}: one instruction fetches kpi k-blocks
+  cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)(K / 64)}; cuuint64_t str[2] = {(cuuint64_t)K * 2, 128};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)kpi}, es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, p, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r) { printf("encode failed %d\n", (int)r); exit(1); }
 }
-template <int BN, int STAGES>
-void run(void* A, void* B, int K, int sms, long long* d_out) {
-  CUtensorMap ta, tb; map2d(&ta, A, K, (long long)sms * 128, 128); map2d(&tb, B, K, 256, BN);
-  const int smem = STAGES * (128 * 128 + BN * 128) + 1024 + 256;
-  cudaFuncSetAttribute(mb_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  const int nkb = 2048;
+template <int BN, int STAGES, int KPI>
+void run(void* A, void* B, int K, int sms, long long* d_out, const char* tag) {
+  printf("-- %s, %d k-block(s) per TMA instruction\n", tag, KPI);
+  CUtensorMap ta, tb; map3d(&ta, A, K, (long long)sms * 128, 128, KPI); map3d(&tb, B, K, 256, BN, KPI);
+  const int smem = STAGES * KPI * (128 * 128 + BN * 128) + 1024 + 256;
+  cudaFuncSetAttribute(mb_kernel<BN, STAGES, KPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int nkb = 2048 / KPI;
   for (int mode = 0; mode < 4; ++mode) {
-    for (int rep = 0; rep < 2; ++rep) mb_kernel<BN, STAGES><<<sms, 128, smem>>>(ta, tb, mode, nkb, K / 64, d_out);
+    for (int rep = 0; rep < 2; ++rep) mb_kernel<BN, STAGES, KPI><<<sms, 128, smem>>>(ta, tb, mode, nkb, K / 64, d_out);
     cudaError_t e = cudaDeviceSynchronize();
     if (e) { printf("mode %d failed: %s\n", mode, cudaGetErrorString(e)); exit(1); }
     std::vector<long long> h(sms); cudaMemcpy(h.data(), d_out, sms * 8, cudaMemcpyDeviceToHost);
     long long mx = 0; for (auto v : h) mx = v > mx ? v : mx;
-    const double cyc = double(mx) / nkb;
+    const double cyc = double(mx) / (nkb * KPI);      // per 64-wide k-block
     printf("BN=%3d stages=%d mode=%d  %.1f cycles/k-block  tensor-util=%.0f%% (ideal %d)  ingest=%.1f B/clk/SM\n", BN, STAGES, mode, cyc,
            100.0 * (2.0 * BN) / cyc, 2 * BN, (128.0 * 128 + BN * 128) / cyc);
   }
@@ -106,8 +112,13 @@ int main() {
   cudaMalloc(&A, (size_t)sms * 128 * K * 2); cudaMalloc(&B, (size_t)256 * K * 2); cudaMalloc(&d_out, sms * 8);
   cudaMemset(A, 0, (size_t)sms * 128 * K * 2); cudaMemset(B, 0, (size_t)256 * K * 2);
   printf("SMs %d\n", sms);
-  run<160, 5>(A, B, K, sms, d_out);
-  run<256, 4>(A, B, K, sms, d_out);
-  run<64, 8>(A, B, K, sms, d_out);
+  run<160, 5, 1>(A, B, 512, sms, d_out, "A L2-resident (K=512: 19 MB total)");
+  run<160, 2, 2>(A, B, 512, sms, d_out, "A L2-resident");
+  run<160, 3, 2>(A, B, 512, sms, d_out, "A L2-resident");
+  run<256, 4, 1>(A, B, 512, sms, d_out, "A L2-resident");
+  run<256, 2, 2>(A, B, 512, sms, d_out, "A L2-resident");
+  run<64, 2, 4>(A, B, 512, sms, d_out, "A L2-resident");
+  run<160, 3, 2>(A, B, K, sms, d_out, "A streams from HBM (310 MB)");
+  run<256, 2, 2>(A, B, K, sms, d_out, "A streams from HBM (310 MB)");
   return 0;
 }
