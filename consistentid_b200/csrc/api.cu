@@ -18,6 +18,7 @@
 #include "gemm_tc2.cuh"
 #include "gemm_tc3.cuh"
 #include "gemm_tc4.cuh"
+#include "gemm_tc5.cuh"
 
 using namespace cid;
 
@@ -104,12 +105,13 @@ int num_sms() {
 }
 // 1 = one-tile-per-CTA kernel (gemm_tc.cuh), 2 = persistent 1-CTA kernel (gemm_tc2.cuh, default),
 // 3 = persistent 2-CTA pairs (gemm_tc3.cuh; parity-green, measured no faster than 2 on B200 - see DESIGN.md),
-// 4 = version 2 with two k-blocks per TMA instruction for the 160/64-wide tiles (gemm_tc4.cuh, default)
+// 4 = version 2 with two k-blocks per TMA instruction for the 160/64-wide tiles (gemm_tc4.cuh; parity-green, ~neutral),
+// 5 = version 2 with the row-coalesced smem-staged epilogue (gemm_tc5.cuh, default)
 int g_gemm_version = 0;
 int gemm_version() {
   if (g_gemm_version == 0) {
     const char* e = getenv("CID_GEMM_VERSION");
-    g_gemm_version = (e && e[0] >= '1' && e[0] <= '4') ? (e[0] - '0') : 4;
+    g_gemm_version = (e && e[0] >= '1' && e[0] <= '5') ? (e[0] - '0') : 5;
   }
   return g_gemm_version;
 }
@@ -151,6 +153,30 @@ int launch_gemm3(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap
 // rows of B staged per CTA (= TMA box height of the weight map)
 int b_box_rows(int bn) { return (gemm_version() == 3 && bn >= 32) ? bn / 2 : bn; }
 
+template <int BN, int STAGES>
+int launch_gemm5(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
+  using SM = Gemm5Smem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    int rc = set_smem(gemm_tc5_kernel<BN, STAGES>, SM::TOTAL, "gemm_tc5_kernel");
+    if (rc) return rc;
+    configured = true;
+  }
+  const int n_tiles = (g.N + BN - 1) / BN;
+  const int total = n_tiles * m_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_tc5_kernel<BN, STAGES><<<grid, GEMM2_THREADS, SM::TOTAL, st>>>(a1, a2, b, g, n_tiles, total);
+  CID_CHECK_LAUNCH("gemm_tc5_kernel");
+  return 0;
+}
+// the coalesced epilogue moves whole 16-byte segments: needs 8-element granularity everywhere
+bool v5_ok(int bn, const GemmArgs& g) {
+  const int n_out = g.epi == EPI_GEGLU ? g.N / 2 : g.N;
+  return gemm_version() == 5 && bn >= 64 && n_out % 8 == 0 && g.ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 &&
+         (!g.residual || (g.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(g.residual) & 15) == 0)) &&
+         (g.epi != EPI_QKV || g.n_split % 8 == 0);
+}
+
 template <int BN, int STAGES, int KPI>
 int launch_gemm4(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
   using SM = Gemm4Smem<BN, STAGES, KPI>;
@@ -189,7 +215,14 @@ int dispatch_gemm(int bn, const CUtensorMap& a1, const CUtensorMap& a2, const CU
     }
     return fail(CID_ERR_UNSUPPORTED, "no 2-CTA GEMM instantiation for tile N %d", bn);
   }
-  if (gemm_version() >= 2) {      // (version 4 falls through to the 1-CTA kernel for tiles it does not cover)
+  if (v5_ok(bn, g)) {
+    switch (bn) {
+      case 256: return launch_gemm5<256, 3>(a1, a2, b, g, m_tiles, st);
+      case 160: return launch_gemm5<160, 4>(a1, a2, b, g, m_tiles, st);
+      case 64: return launch_gemm5<64, 8>(a1, a2, b, g, m_tiles, st);
+    }
+  }
+  if (gemm_version() >= 2) {      // (versions 4 / 5 fall through to the v2 kernel for tiles they do not cover)
     switch (bn) {
       case 256: return launch_gemm2<256, 4>(a1, a2, b, g, m_tiles, st);
       case 160: return launch_gemm2<160, 5>(a1, a2, b, g, m_tiles, st);

@@ -9,6 +9,7 @@
 // A stage therefore holds KPI k-blocks: [A chunk 0 | A chunk 1 | B chunk 0 | B chunk 1]; odd k-block counts (K=320 -> 5)
 // leave the last chunk zero-filled by TMA and the MMA issuer simply skips it.
 #pragma once
+#include <type_traits>
 #include "gemm_tc2.cuh"
 
 namespace cid {
@@ -147,12 +148,14 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     }
   } else {
     // ================================================================ epilogue (warps 2..9)
+    // (generic lambda: the 16-bit flavour becomes a compile-time constant, so pack/unpack fold to one conversion)
+    auto epilogue = [&](auto bf_tag) {
+    constexpr int bf = decltype(bf_tag)::value;
     const int ew = warp - 2;
     const int quarter = warp & 3;
     const int half = ew >> 2;                              // which half of the tile's columns this warp drains
     const int r = quarter * 32 + lane;
     const int et = threadIdx.x - 64;                       // 0..255
-    const int bf = g.is_bf16;
     const bool geglu = g.epi == EPI_GEGLU;
     // column range [c_beg, c_end) in 16-column chunks (GEGLU: over the value half only)
     constexpr int NCHUNK = BN / 16;
@@ -219,8 +222,7 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
               for (int j = 0; j < 16; j += 2) {
                 const float v0 = __uint_as_float(a[j]) + bs[ch * 16 + j], v1 = __uint_as_float(a[j + 1]) + bs[ch * 16 + j + 1];
                 const float g0 = __uint_as_float(b[j]) + bs[HALF + ch * 16 + j], g1 = __uint_as_float(b[j + 1]) + bs[HALF + ch * 16 + j + 1];
-                const float2 vr = unpack16(pack16(v0, v1, bf), bf), gr = unpack16(pack16(g0, g1, bf), bf);
-                packed[j >> 1] = pack16(vr.x * gelu_erf(gr.x), vr.y * gelu_erf(gr.y), bf);
+                packed[j >> 1] = pack16(v0 * gelu_erf(g0), v1 * gelu_erf(g1), bf);
               }
               uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(g.C) + grow * g.ldc + out_col0 + ch * 16);
               dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -299,6 +301,8 @@ gemm_tc4_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
       tc_fence_before();
       mbar_arrive(acc_empty(ab));                           // this thread no longer reads accumulator `ab`
     }
+    };
+    if (g.is_bf16) epilogue(std::integral_constant<int, 1>{}); else epilogue(std::integral_constant<int, 0>{});
   }
 
   __syncthreads();

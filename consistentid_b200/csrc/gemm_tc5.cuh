@@ -1,42 +1,42 @@
-// Persistent tcgen05 GEMM / implicit-GEMM conv3x3 (v2 of gemm_tc.cuh; same arguments, same math).
+// gemm_tc5_kernel - gemm_tc2.cuh with a ROW-COALESCED epilogue (v5; same arguments, math and main loop).
 //
-// One CTA per SM loops over output tiles (tile = blockIdx.x + i*gridDim.x, N-tile fastest so CTAs running at the same
-// time share the activation (A) tile in L2).  Roles (320 threads):
-//   warp 0      TMA producer - keeps the STAGES-deep smem ring full ACROSS tile boundaries
-//   warp 1      TMEM allocator (512 columns = two accumulators) + tcgen05.mma issuer; alternates accumulators so the
-//               main loop of tile i+1 overlaps the epilogue of tile i
-//   warps 2-9   epilogue: two warps per TMEM lane quarter, each draining half of the tile's columns in 16-column
-//               tcgen05.ld chunks; residual rows are prefetched into registers BEFORE waiting for the accumulator and the
-//               bias slice of the tile is staged once in smem, so no global-load latency sits between TMEM and the stores
+// Why: for the small-K GEMMs that dominate SD1.5 (K = 320: five k-blocks) a tile took ~10k cycles against ~3k of main loop.
+// In the v2 epilogue every lane owns one accumulator ROW, so each 16-byte store (and residual load) of a warp touches 32
+// different 128-byte lines: 2560 LSU wavefronts per 128x160 tile each way.  v5 stages the tile through shared memory:
+//   phase 1  (lane = row)    tcgen05.ld 16 columns, + bias (+ per-sample time-embedding bias, GEGLU), round to 16-bit exactly where
+//                            the reference rounds its Linear output, write 32 bytes into a padded row-major smem tile;
+//                            the TMEM accumulator is released right after this phase
+//   phase 2  (lane = column) each warp takes 16 rows; lanes read consecutive 16-byte segments of a row from smem, load the residual
+//                            row COALESCED, add, store COALESCED: 320 wavefronts per tile instead of 2560.
+// V columns of the QKV epilogue keep their direct transposed stores (already lane-contiguous).  Tiles whose width is not a
+// multiple of 8 columns (conv_out: 4 channels) use the v2 kernel.
 #pragma once
 #include <type_traits>
-#include "elementwise.cuh"
-#include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 
 namespace cid {
 
-constexpr int GEMM2_THREADS = 320;
-constexpr int GEMM2_EPI_THREADS = 256;
 
 template <int BN, int STAGES>
-struct Gemm2Smem {
+struct Gemm5Smem {
   static constexpr int A_BYTES = GEMM_BM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int BIAS_OFF = BAR_OFF + 256;             // 2 x BN floats
-  static constexpr int TOTAL = BIAS_OFF + 2 * BN * 4 + 1024;
+  static constexpr int OUT_PITCH = BN * 2 + 16;              // padded row pitch (bytes) of the output staging tile
+  static constexpr int OUT_OFF = (BIAS_OFF + 2 * BN * 4 + 15) / 16 * 16;
+  static constexpr int TOTAL = OUT_OFF + GEMM_BM * OUT_PITCH + 1024;
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM2_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmB, const GemmArgs g, const int n_tiles, const int total_tiles) {
   static_assert(BN % 32 == 0 || BN == 16, "column split");
   constexpr int ACC_STRIDE = 256;                              // TMEM column offset between the two accumulators
-  using SM = Gemm2Smem<BN, STAGES>;
+  using SM = Gemm5Smem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -142,158 +142,141 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     }
   } else {
     // ================================================================ epilogue (warps 2..9)
-    // (generic lambda: the 16-bit flavour becomes a compile-time constant, so pack/unpack fold to one conversion)
     auto epilogue = [&](auto bf_tag) {
     constexpr int bf = decltype(bf_tag)::value;
     const int ew = warp - 2;
     const int quarter = warp & 3;
-    const int half = ew >> 2;                              // which half of the tile's columns this warp drains
+    const int half = ew >> 2;                              // which half of the tile's columns this warp drains in phase 1
     const int r = quarter * 32 + lane;
     const int et = threadIdx.x - 64;                       // 0..255
     const bool geglu = g.epi == EPI_GEGLU;
-    // column range [c_beg, c_end) in 16-column chunks (GEGLU: over the value half only)
     constexpr int NCHUNK = BN / 16;
     constexpr int NCHUNK_G = (BN / 2) / 16 > 0 ? (BN / 2) / 16 : 1;
     const int nch = geglu ? NCHUNK_G : NCHUNK;
     const int ch_beg = half == 0 ? 0 : (nch + 1) / 2;
     const int ch_end = half == 0 ? (nch + 1) / 2 : nch;
     constexpr int MAXCH = (NCHUNK + 1) / 2;
+    uint8_t* out_s = smem_gen + SM::OUT_OFF;
+    // global row of tile row `rr` (and whether it exists)
+    auto row_of = [&](int mt, int rr, long long& grow) -> bool {
+      if (g.a_mode == A_GEMM) { grow = (long long)mt * GEMM_BM + rr; return grow < g.M; }
+      int tn0, ty0, tx0;
+      tile_origin(mt, tn0, ty0, tx0);
+      const int per_img = g.TW * g.TH;
+      const int dn = rr / per_img, rem = rr - dn * per_img;
+      const int dy = rem / g.TW, dx = rem - dy * g.TW;
+      const int n = tn0 + dn, y = ty0 + dy, x = tx0 + dx;
+      grow = ((long long)n * g.H + y) * g.W + x;
+      return (dn < g.TN) && (n < g.NB) && (y < g.H) && (x < g.W);
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int ab = it & 1;
       const uint32_t aphase = uint32_t(it >> 1) & 1u;
       const int nt = tile % n_tiles, mt = tile / n_tiles;
       const int n0 = nt * BN;
-      long long grow; bool row_ok;
-      if (g.a_mode == A_GEMM) {
-        grow = (long long)mt * GEMM_BM + r;
-        row_ok = grow < g.M;
-      } else {
-        int tn0, ty0, tx0;
-        tile_origin(mt, tn0, ty0, tx0);
-        const int per_img = g.TW * g.TH;
-        const int dn = r / per_img, rem = r - dn * per_img;
-        const int dy = rem / g.TW, dx = rem - dy * g.TW;
-        const int n = tn0 + dn, y = ty0 + dy, x = tx0 + dx;
-        row_ok = (dn < g.TN) && (n < g.NB) && (y < g.H) && (x < g.W);
-        grow = ((long long)n * g.H + y) * g.W + x;
-      }
-      // stage this tile's bias slice (fp32) in smem; buffer alternates with the accumulator
+      long long grow;
+      const bool row_ok = row_of(mt, r, grow);
+      // output-tile geometry: first global column, width staged through smem (QKV: only the non-V columns)
+      const int out_col0 = geglu ? nt * (BN / 2) : n0;
+      const int out_n = geglu ? g.N / 2 : g.N;
+      int w_stage = geglu ? BN / 2 : BN;
+      if (g.epi == EPI_QKV) { const int lim = g.n_split - n0; w_stage = lim < 0 ? 0 : (lim < BN ? lim : BN); }
+      if (out_col0 + w_stage > out_n) w_stage = out_n - out_col0 > 0 ? out_n - out_col0 : 0;
       float* bs = bias_s + ab * BN;
       for (int j = et; j < BN; j += GEMM2_EPI_THREADS) bs[j] = (g.bias && n0 + j < g.N) ? load16(g.bias, n0 + j, bf) : 0.f;
-      // prefetch residual rows for this thread's chunks (latency overlaps the wait for the accumulator)
-      uint4 res[MAXCH][2];
-      const bool use_res = g.residual != nullptr && !geglu && row_ok;
-      const uint16_t* rrow = use_res ? reinterpret_cast<const uint16_t*>(g.residual) + grow * g.ldr + n0 : nullptr;
-      const bool res_vec = use_res && ((reinterpret_cast<uintptr_t>(rrow) & 15) == 0) && (n0 + BN <= g.N);
-#pragma unroll
-      for (int c = 0; c < MAXCH; ++c) {
-        const int ch = ch_beg + c;
-        if (res_vec && ch < ch_end) {
-          res[c][0] = reinterpret_cast<const uint4*>(rrow + ch * 16)[0];
-          res[c][1] = reinterpret_cast<const uint4*>(rrow + ch * 16)[1];
-        }
-      }
-      epi_bar_sync();                                       // bias slice visible to all epilogue threads
+      epi_bar_sync();                                       // bias slice visible; previous tile's phase 2 finished with out_s
       mbar_wait(acc_full(ab), aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ab * ACC_STRIDE + (uint32_t(quarter * 32) << 16);
-
-      if (BN >= 32 && geglu) {
-        constexpr int HALF = BN / 2;
-        const int out_col0 = nt * HALF;
+      uint8_t* my_row = out_s + r * SM::OUT_PITCH;
+      // ---------------- phase 1: TMEM -> (+bias, activation) -> 16-bit -> smem tile (lane = row)
 #pragma unroll
-        for (int c = 0; c < MAXCH; ++c) {
-          const int ch = ch_beg + c;
-          if (ch < ch_end) {
+      for (int c = 0; c < MAXCH; ++c) {
+        const int ch = ch_beg + c;
+        if (ch < ch_end) {
+          float v[16];
+          if (BN >= 32 && geglu) {
+            constexpr int HALF = BN / 2;
             uint32_t a[16], b[16];
             tmem_ld_x16(t_row + ch * 16, a);
             tmem_ld_x16(t_row + HALF + ch * 16, b);
             tmem_ld_wait();
-            if (row_ok) {
-              uint32_t packed[8];
 #pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                const float v0 = __uint_as_float(a[j]) + bs[ch * 16 + j], v1 = __uint_as_float(a[j + 1]) + bs[ch * 16 + j + 1];
-                const float g0 = __uint_as_float(b[j]) + bs[HALF + ch * 16 + j], g1 = __uint_as_float(b[j + 1]) + bs[HALF + ch * 16 + j + 1];
-                packed[j >> 1] = pack16(v0 * gelu_erf(g0), v1 * gelu_erf(g1), bf);
-              }
-              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(g.C) + grow * g.ldc + out_col0 + ch * 16);
-              dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-              dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-            }
-          }
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < MAXCH; ++c) {
-          const int ch = ch_beg + c;
-          if (ch < ch_end) {
+            for (int j = 0; j < 16; ++j)
+              v[j] = (__uint_as_float(a[j]) + bs[ch * 16 + j]) * gelu_erf(__uint_as_float(b[j]) + bs[HALF + ch * 16 + j]);
+          } else {
             uint32_t a[16];
             tmem_ld_x16(t_row + ch * 16, a);
             tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(a[j]) + bs[ch * 16 + j];
             const int col0 = n0 + ch * 16;
-            if (row_ok && col0 < g.N) {
-              const bool full = (col0 + 16 <= g.N);
-              float v[16];
+            if (g.rowbias && row_ok && col0 < g.N) {
+              const uint16_t* rb = reinterpret_cast<const uint16_t*>(g.rowbias) + (grow / g.rows_per_group) * g.ld_rowbias + col0;
+              if (col0 + 16 <= g.N && ((reinterpret_cast<uintptr_t>(rb) & 15) == 0)) {
+                float f0[8], f1[8];
+                unpack8(reinterpret_cast<const uint4*>(rb)[0], f0, bf); unpack8(reinterpret_cast<const uint4*>(rb)[1], f1, bf);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(a[j]) + bs[ch * 16 + j];
-              if (g.rowbias) {
-                const uint16_t* rb = reinterpret_cast<const uint16_t*>(g.rowbias) + (grow / g.rows_per_group) * g.ld_rowbias + col0;
-                if (full && ((reinterpret_cast<uintptr_t>(rb) & 15) == 0)) {
-                  float f0[8], f1[8];
-                  unpack8(reinterpret_cast<const uint4*>(rb)[0], f0, bf); unpack8(reinterpret_cast<const uint4*>(rb)[1], f1, bf);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) { v[j] += f0[j]; v[8 + j] += f1[j]; }
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) if (full || col0 + j < g.N) v[j] += load16(rb, j, bf);
-                }
-              }
-              if (g.epi == EPI_QKV && col0 >= g.n_split) {
-                const int b = int(grow / g.ntok), tok = int(grow - (long long)b * g.ntok);
-          const size_t vC = (size_t)g.heads * g.hdim;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int vc = col0 + j - g.n_split;
-                  if (full || col0 + j < g.N) {
-                    store16(g.Vt, ((size_t)b * vC + vc) * g.ntok + tok, v[j], bf);   // (b*heads + h)*hdim + dd == b*C + vc
-                  }
-                }
+                for (int j = 0; j < 8; ++j) { v[j] += f0[j]; v[8 + j] += f1[j]; }
               } else {
-                if (use_res) {
-                  if (res_vec) {
-                    float f0[8], f1[8];
-                    unpack8(res[c][0], f0, bf); unpack8(res[c][1], f1, bf);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) { v[j] += f0[j]; v[8 + j] += f1[j]; }
-                  } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) if (full || col0 + j < g.N) v[j] += load16(rrow, ch * 16 + j, bf);
-                  }
-                }
-                if (g.out_scale != 1.0f) {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) v[j] *= g.out_scale;
-                }
-                uint16_t* crow = reinterpret_cast<uint16_t*>(g.C) + grow * g.ldc + col0;
-                if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
-                  float lo[8], hi[8];
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
-                  reinterpret_cast<uint4*>(crow)[0] = pack8(lo, bf);
-                  reinterpret_cast<uint4*>(crow)[1] = pack8(hi, bf);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) if (full || col0 + j < g.N) store16(crow, j, v[j], bf);
-                }
+                for (int j = 0; j < 16; ++j) if (col0 + j < g.N) v[j] += load16(rb, j, bf);
               }
             }
+            if (g.epi == EPI_QKV && col0 >= g.n_split) {
+              // V columns: transposed store Vt[(b*C + vc), tok]; lanes hold consecutive tokens -> already contiguous
+              if (row_ok && col0 < g.N) {
+                const int b = int(grow / g.ntok), tok = int(grow - (long long)b * g.ntok);
+                const size_t vC = (size_t)g.heads * g.hdim;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (col0 + j < g.N) store16(g.Vt, ((size_t)b * vC + (col0 + j - g.n_split)) * g.ntok + tok, v[j], bf);
+              }
+              continue;
+            }
           }
+          float lo[8], hi[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+          reinterpret_cast<uint4*>(my_row + ch * 32)[0] = pack8(lo, bf);
+          reinterpret_cast<uint4*>(my_row + ch * 32)[1] = pack8(hi, bf);
         }
       }
       tc_fence_before();
-      mbar_arrive(acc_empty(ab));                           // this thread no longer reads accumulator `ab`
+      mbar_arrive(acc_empty(ab));                           // accumulator fully read: the next tile's MMAs may start
+      epi_bar_sync();                                       // whole staging tile written
+      // ---------------- phase 2: smem tile -> (+residual) -> global, row-coalesced (lane = 8-column segment)
+      const int segs = w_stage >> 3;                        // 16-byte segments per row
+      if (segs > 0) {
+#pragma unroll 1
+        for (int rr = ew; rr < GEMM_BM; rr += 8) {
+          long long gr;
+          if (!row_of(mt, rr, gr)) continue;
+          const uint8_t* srow = out_s + rr * SM::OUT_PITCH;
+          uint16_t* crow = reinterpret_cast<uint16_t*>(g.C) + gr * g.ldc + out_col0;
+          const uint16_t* rrow = g.residual ? reinterpret_cast<const uint16_t*>(g.residual) + gr * g.ldr + out_col0 : nullptr;
+          for (int sgi = lane; sgi < segs; sgi += 32) {
+            uint4 u = *reinterpret_cast<const uint4*>(srow + sgi * 16);
+            if (rrow || g.out_scale != 1.0f) {
+              float f[8];
+              unpack8(u, f, bf);
+              if (rrow) {
+                float q[8];
+                unpack8(*reinterpret_cast<const uint4*>(rrow + sgi * 8), q, bf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += q[j];
+              }
+              if (g.out_scale != 1.0f) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] *= g.out_scale;
+              }
+              u = pack8(f, bf);
+            }
+            *reinterpret_cast<uint4*>(crow + sgi * 8) = u;
+          }
+        }
+      }
     }
     };
     if (g.is_bf16) epilogue(std::integral_constant<int, 1>{}); else epilogue(std::integral_constant<int, 0>{});
