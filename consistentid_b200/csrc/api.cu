@@ -103,15 +103,15 @@ int num_sms() {
   }
   return g_num_sms;
 }
-// 1 = one-tile-per-CTA kernel (gemm_tc.cuh), 2 = persistent 1-CTA kernel (gemm_tc2.cuh, default),
+// 1 = one-tile-per-CTA kernel (gemm_tc.cuh), 2 = persistent 1-CTA kernel (gemm_tc2.cuh, DEFAULT),
 // 3 = persistent 2-CTA pairs (gemm_tc3.cuh; parity-green, measured no faster than 2 on B200 - see DESIGN.md),
 // 4 = version 2 with two k-blocks per TMA instruction for the 160/64-wide tiles (gemm_tc4.cuh; parity-green, ~neutral),
-// 5 = version 2 with the row-coalesced smem-staged epilogue (gemm_tc5.cuh, default)
+// 5 = version 2 with a row-coalesced smem-staged epilogue (gemm_tc5.cuh; parity-green, measured SLOWER except for the QKV epilogue)
 int g_gemm_version = 0;
 int gemm_version() {
   if (g_gemm_version == 0) {
     const char* e = getenv("CID_GEMM_VERSION");
-    g_gemm_version = (e && e[0] >= '1' && e[0] <= '5') ? (e[0] - '0') : 5;
+    g_gemm_version = (e && e[0] >= '1' && e[0] <= '5') ? (e[0] - '0') : 2;
   }
   return g_gemm_version;
 }
@@ -422,9 +422,15 @@ int cid_attn_self(const void* Q, long long q_pitch, const void* K, long long k_p
   CUtensorMap tq, tk, tv; int rc;
   if ((rc = map_qk(&tq, Q, B, N, H, d, q_pitch, 128))) return rc;
   if ((rc = map_qk(&tk, K, B, N, H, d, k_pitch, 128))) return rc;
-  if ((rc = map_vt(&tv, Vt, B * H, d, N, dp))) return rc;
   AttnArgs a{}; a.B = B; a.H = H; a.Nq = N; a.Nkv = N; a.d = d; a.scale_log2 = 1.4426950408889634f / sqrtf(float(d));
   a.O = O; a.ldo = ldo; a.is_bf16 = dtype == CID_BF16;
+  if (attn_version() == 3 && N % 128 == 0) {      // every tile has both 64-key chunks: fetch them with one 4-D box (TMA cost is per instruction)
+    cuuint64_t dims[4] = {64, cuuint64_t(d), cuuint64_t(N / 64), cuuint64_t(B) * H};
+    cuuint64_t str[3] = {cuuint64_t(N) * 2, 128, cuuint64_t(N) * cuuint64_t(d) * 2};
+    cuuint32_t box[4] = {64, cuuint32_t(dp), 2, 1};
+    if ((rc = make_map(&tv, Vt, 4, dims, str, box))) return rc;
+    a.vt4d = 1;
+  } else if ((rc = map_vt(&tv, Vt, B * H, d, N, dp))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (attn_version() == 3) {
     switch (dp) {

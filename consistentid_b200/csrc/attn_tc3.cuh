@@ -89,8 +89,12 @@ attn_self3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           tma_load_4d(sbase + C::OFF_K + stage * C::K_BYTES + ch * 16384, &tmK, k_full(stage), ch * 64, k0, h, b);
         mbar_wait(v_empty(stage), phase ^ 1u);
         mbar_expect_tx(v_full(stage), C::V_BYTES);
-        for (int kc = 0; kc < 2; ++kc)
-          tma_load_3d(sbase + C::OFF_V + stage * C::V_BYTES + kc * C::V_CHUNK, &tmVt, v_full(stage), k0 + kc * 64, 0, b * a.H + h);
+        if (a.vt4d) {
+          tma_load_4d(sbase + C::OFF_V + stage * C::V_BYTES, &tmVt, v_full(stage), 0, 0, k0 >> 6, b * a.H + h);   // box {64, D_PAD, 2, 1}
+        } else {
+          for (int kc = 0; kc < 2; ++kc)
+            tma_load_3d(sbase + C::OFF_V + stage * C::V_BYTES + kc * C::V_CHUNK, &tmVt, v_full(stage), k0 + kc * 64, 0, b * a.H + h);
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
