@@ -424,7 +424,7 @@ int cid_attn_self(const void* Q, long long q_pitch, const void* K, long long k_p
   if ((rc = map_qk(&tk, K, B, N, H, d, k_pitch, 128))) return rc;
   AttnArgs a{}; a.B = B; a.H = H; a.Nq = N; a.Nkv = N; a.d = d; a.scale_log2 = 1.4426950408889634f / sqrtf(float(d));
   a.O = O; a.ldo = ldo; a.is_bf16 = dtype == CID_BF16;
-  if (attn_version() == 3 && N % 128 == 0) {      // every tile has both 64-key chunks: fetch them with one 4-D box (TMA cost is per instruction)
+  if (false && attn_version() == 3 && N % 128 == 0) {   // DISABLED: one 4-D box for both 64-key chunks - no measured gain and two battery configs timed out
     cuuint64_t dims[4] = {64, cuuint64_t(d), cuuint64_t(N / 64), cuuint64_t(B) * H};
     cuuint64_t str[3] = {cuuint64_t(N) * 2, 128, cuuint64_t(N) * cuuint64_t(d) * 2};
     cuuint32_t box[4] = {64, cuuint32_t(dp), 2, 1};
