@@ -171,32 +171,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
       grow_ = ((long long)n * g.H + y) * g.W + x;
       return (dn < g.TN) && (n < g.NB) && (y < g.H) && (x < g.W);
     };
-    // Residual rows are prefetched ONE TILE AHEAD: ncu showed the epilogue of the small-K GEMMs stalled on these
-    // (row-scattered, DRAM-latency) loads when they were issued at the start of the same tile.
-    struct ResPref { const uint16_t* rrow; bool use, vec; };
-    auto issue_res = [&](int tile_, uint4 (&dst)[MAXCH][2]) -> ResPref {
-      ResPref p{nullptr, false, false};
-      if (g.residual == nullptr || geglu || tile_ >= total_tiles) return p;
-      long long gr;
-      if (!my_row(tile_, gr)) return p;
-      const int n0_ = (tile_ % n_tiles) * BN;
-      p.use = true;
-      p.rrow = reinterpret_cast<const uint16_t*>(g.residual) + gr * g.ldr + n0_;
-      p.vec = ((reinterpret_cast<uintptr_t>(p.rrow) & 15) == 0) && (n0_ + BN <= g.N);
-      if (p.vec) {
-#pragma unroll
-        for (int c = 0; c < MAXCH; ++c) {
-          const int ch = ch_beg + c;
-          if (ch < ch_end) {
-            dst[c][0] = reinterpret_cast<const uint4*>(p.rrow + ch * 16)[0];
-            dst[c][1] = reinterpret_cast<const uint4*>(p.rrow + ch * 16)[1];
-          }
-        }
-      }
-      return p;
-    };
-    uint4 res[MAXCH][2], nres[MAXCH][2];
-    ResPref cur = issue_res(blockIdx.x, res);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int ab = it & 1;
@@ -209,10 +183,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
       // stage this tile's bias slice (fp32) in smem; buffer alternates with the accumulator
       float* bs = bias_s + ab * BN;
       for (int j = et; j < BN; j += GEMM2_EPI_THREADS) bs[j] = (g.bias && n0 + j < g.N) ? load16(g.bias, n0 + j, bf) : 0.f;
-      const ResPref nxt = issue_res(tile + gridDim.x, nres);       // next tile's residual rows: a whole tile of latency hiding
-      const bool use_res = cur.use;
-      const uint16_t* rrow = cur.rrow;
-      const bool res_vec = cur.vec;
+      // prefetch residual rows for this thread's chunks (latency overlaps the wait for the accumulator; prefetching a whole
+      // tile ahead was measured: no gain at BN=160, register spills at BN=256)
+      uint4 res[MAXCH][2];
+      const bool use_res = g.residual != nullptr && !geglu && row_ok;
+      const uint16_t* rrow = use_res ? reinterpret_cast<const uint16_t*>(g.residual) + grow * g.ldr + n0 : nullptr;
+      const bool res_vec = use_res && ((reinterpret_cast<uintptr_t>(rrow) & 15) == 0) && (n0 + BN <= g.N);
+#pragma unroll
+      for (int c = 0; c < MAXCH; ++c) {
+        const int ch = ch_beg + c;
+        if (res_vec && ch < ch_end) {
+          res[c][0] = reinterpret_cast<const uint4*>(rrow + ch * 16)[0];
+          res[c][1] = reinterpret_cast<const uint4*>(rrow + ch * 16)[1];
+        }
+      }
       epi_bar_sync();                                       // bias slice visible to all epilogue threads
       mbar_wait(acc_full(ab), aphase);
       tc_fence_after();
@@ -313,9 +297,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
       }
       tc_fence_before();
       mbar_arrive(acc_empty(ab));                           // this thread no longer reads accumulator `ab`
-      cur = nxt;
-#pragma unroll
-      for (int c = 0; c < MAXCH; ++c) { res[c][0] = nres[c][0]; res[c][1] = nres[c][1]; }
     }
     };
     if (g.is_bf16) epilogue(std::integral_constant<int, 1>{}); else epilogue(std::integral_constant<int, 0>{});
