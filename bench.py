@@ -303,9 +303,13 @@ def run_ours(args):
             res["kernels"] = {k: dict(launches=v["launches"], ms=round(v["ms"], 3), tflops=round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1))
                               for k, v in agg.items()}
             achieved = tc["flops"] / max(tc["ms"], 1e-9) / 1e9
+            traffic = None      # committed ncu dram__bytes capture of the same eager step (tools/summarize_dram.py), bytes per launch
+            tpath = os.path.join(ROOT, "profiles", f"r01_dram_traffic_{args.workload}.json")
+            if os.path.exists(tpath):
+                traffic = round(json.load(open(tpath))["tensor_core_kernels"]["bytes_per_launch"])
             res["roofline"] = {"kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)", "bound": "tensor", "achieved": round(achieved, 1),
                                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(achieved / pk["tf_sustained"], 4),
-                               "traffic": None, "peak_src": pk["src"] + " (sustained bf16 GEMM)", "launches_timed": tc["launches"],
+                               "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)", "peak_src": pk["src"] + " (sustained bf16 GEMM)", "launches_timed": tc["launches"],
                                "avg_launch_ms": round(tc["ms"] / max(tc["launches"], 1), 4),
                                "alg_flops_per_launch": round(tc["flops"] / max(tc["launches"], 1) / 1e9, 2), "alg_flops_unit": "GFLOP"}
             if "attn_self" in agg:

@@ -116,6 +116,12 @@ class B200Scheduler:
         return SimpleNamespace(prev_sample=prev.to(sample.dtype), pred_original_sample=x0.to(sample.dtype))
 
     def add_noise(self, original_samples, noise, timesteps):
+        if self.kind == "euler":        # sigma parameterisation: x + sigma(t) * noise, t must be one of self.timesteps
+            sig = torch.tensor([self.sigmas[self._index(t)] for t in torch.as_tensor(timesteps).reshape(-1).tolist()],
+                               dtype=torch.float32, device=original_samples.device)
+            while sig.ndim < original_samples.ndim:
+                sig = sig[..., None]
+            return (original_samples.float() + sig * noise.float()).to(original_samples.dtype)
         a = torch.from_numpy(self.acp).to(original_samples.device)[timesteps.long()].to(torch.float32)
         while a.ndim < original_samples.ndim:
             a = a[..., None]

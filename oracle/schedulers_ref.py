@@ -84,6 +84,13 @@ class EulerRef(_Base):
         s = self.sigmas[self._index(t)]
         return x / ((s ** 2 + 1) ** 0.5)
 
+    def add_noise(self, x0, noise, timesteps):
+        """EulerDiscreteScheduler.add_noise (diffusers 0.23): x0 + sigma[index of t in self.timesteps] * noise."""
+        sig = torch.stack([self.sigmas[self._index(t)] for t in torch.as_tensor(timesteps).reshape(-1)]).to(x0.dtype)
+        while sig.ndim < x0.ndim:
+            sig = sig[..., None]
+        return x0 + noise * sig
+
     def step(self, eps, t, x, **kw):
         i = self._index(t)
         s, s_next = self.sigmas[i], self.sigmas[i + 1]

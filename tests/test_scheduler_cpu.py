@@ -34,3 +34,11 @@ def test_add_noise():
     x0, n = torch.randn(2, 4, 4, 4), torch.randn(2, 4, 4, 4)
     t = torch.tensor([10, 500])
     assert torch.allclose(ref.add_noise(x0, n, t), ours.add_noise(x0, n, t), atol=1e-5)
+
+
+def test_add_noise_euler():
+    ref = make_scheduler("euler"); ours = sched.B200Scheduler("euler")
+    ref.set_timesteps(20); ours.set_timesteps(20)
+    x0, n = torch.randn(2, 4, 4, 4), torch.randn(2, 4, 4, 4)
+    t = ref.timesteps[[3, 17]]
+    assert torch.allclose(ref.add_noise(x0, n, t), ours.add_noise(x0, n, t), rtol=1e-5, atol=1e-5)
