@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 ( timeout 600 python bench.py --workload sdxl --steps 3 --warmup 3 --no-cpu > gpurun_out/final_bench_sdxl.json 2> gpurun_out/final_bench_sdxl.err )
 ( timeout 600 python bench.py --workload sd15_cn --steps 3 --warmup 3 --no-cpu > gpurun_out/final_bench_sd15_cn.json 2> gpurun_out/final_bench_sd15_cn.err )
 for wl in sd15 sdxl; do
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/final_launches_$wl.csv python tools/profile_step.py $wl 2 > gpurun_out/final_prof_$wl.log 2>&1
-  timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 800 --csv --log-file gpurun_out/final_dram_$wl.csv python tools/profile_step.py $wl 1 > gpurun_out/final_dram_$wl.log 2>&1
+  timeout 600 ncu --kernel-name-base demangled -k regex:cid:: --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/final_launches_$wl.csv python tools/profile_step.py $wl 2 > gpurun_out/final_prof_$wl.log 2>&1
+  timeout 600 ncu --kernel-name-base demangled -k regex:cid:: --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 800 --csv --log-file gpurun_out/final_dram_$wl.csv python tools/profile_step.py $wl 1 > gpurun_out/final_dram_$wl.log 2>&1
 done
 tail -3 gpurun_out/final_pytest.log; cat gpurun_out/final_smoke.log | tail -1; cat gpurun_out/final_bench_sd15.json | cut -c1-400; cat gpurun_out/final_bench_sdxl.json | cut -c1-300; cat gpurun_out/final_bench_sd15_cn.json | cut -c1-300
