@@ -14,6 +14,7 @@
 #include "attn_tc2.cuh"
 #include "attn_tc3.cuh"
 #include "elementwise.cuh"
+#include "embed.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "gemm_tc3.cuh"
@@ -596,11 +597,12 @@ int cid_timestep_embed(const float* t_dev, int t_stride, int rows, int dim, void
 }
 int cid_skinny_linear(const void* x, long long ldx, const void* W, const void* bias, void* y, long long ldy, int M, int N, int K,
                       int silu_in, int accumulate, int dtype, void* stream) {
-  if (!x || !W || !y || K % 8 || K > 4096 || M <= 0) return fail(CID_ERR_ARG, "cid_skinny_linear: K=%d must be a multiple of 8 and <= 4096", K);
+  if (!x || !W || !y || K % 8 || K > 8192 || M <= 0) return fail(CID_ERR_ARG, "cid_skinny_linear: K=%d must be a multiple of 8 and <= 8192", K);
+  const int slab = K <= 4096 ? 16 : 8;           // rows of x staged per pass: slab * K * 2 bytes of shared memory (<= 128 KB)
   static bool configured = false;
   if (!configured) { int rc = set_smem(skinny_linear_kernel, 16 * 4096 * 2, "skinny_linear_kernel"); if (rc) return rc; configured = true; }
-  skinny_linear_kernel<<<(N + 7) / 8, 256, 16 * K * 2, static_cast<cudaStream_t>(stream)>>>(
-      (const uint16_t*)x, ldx, (const uint16_t*)W, (const uint16_t*)bias, (uint16_t*)y, ldy, M, N, K, silu_in, accumulate, dtype == CID_BF16);
+  skinny_linear_kernel<<<(N + 7) / 8, 256, (size_t)slab * K * 2, static_cast<cudaStream_t>(stream)>>>(
+      (const uint16_t*)x, ldx, (const uint16_t*)W, (const uint16_t*)bias, (uint16_t*)y, ldy, M, N, K, silu_in, accumulate, dtype == CID_BF16, slab);
   CID_CHECK_LAUNCH("skinny_linear_kernel");
   return 0;
 }
@@ -624,6 +626,29 @@ int cid_advance_step(int* step_dev, float* t_dev, const float* ts_table, int n, 
   if (!step_dev || !t_dev || !ts_table || n <= 0) return fail(CID_ERR_ARG, "cid_advance_step: bad arguments");
   advance_step_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(step_dev, t_dev, ts_table, n);
   CID_CHECK_LAUNCH("advance_step_kernel");
+  return 0;
+}
+
+int cid_layernorm_rows(const void* x, long long ldx, long long x_group_rows, long long x_row0, const void* gamma, const void* beta, void* y,
+                       long long ldy, long long y_group_rows, long long y_row0, long long rows, long long rows_per_group, int C, float eps,
+                       int dtype, void* stream) {
+  if (!x || !gamma || !beta || !y || C <= 0 || C % 8 || ldx % 8 || ldy % 8 || rows_per_group <= 0)
+    return fail(CID_ERR_ARG, "cid_layernorm_rows: C=%d, ldx, ldy must be multiples of 8 and rows_per_group > 0", C);
+  if (rows <= 0) return 0;
+  layernorm_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      (const uint16_t*)x, ldx, x_group_rows, x_row0, (const uint16_t*)gamma, (const uint16_t*)beta, (uint16_t*)y, ldy, y_group_rows, y_row0, rows,
+      rows_per_group, C, eps, dtype == CID_BF16);
+  CID_CHECK_LAUNCH("layernorm_rows_kernel");
+  return 0;
+}
+
+int cid_perceiver_attn(const void* q, long long ldq, const void* kv, long long ldkv, void* out, long long ldo, int B, int L, int n_kv, int heads,
+                       int dim_head, int dtype, void* stream) {
+  if (!q || !kv || !out || dim_head != 64 || B <= 0 || L <= 0 || heads <= 0 || n_kv <= 0 || n_kv > 8192 || ldkv % 8)
+    return fail(CID_ERR_ARG, "cid_perceiver_attn: dim_head must be 64, 0 < n_kv <= 8192, ldkv %% 8 == 0 (got dim_head=%d n_kv=%d)", dim_head, n_kv);
+  perceiver_attn_kernel<<<(unsigned)(B * L * heads), 128, (size_t)n_kv * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      (const uint16_t*)q, ldq, (const uint16_t*)kv, ldkv, (uint16_t*)out, ldo, L, n_kv, heads, dtype == CID_BF16);
+  CID_CHECK_LAUNCH("perceiver_attn_kernel");
   return 0;
 }
 

@@ -288,21 +288,23 @@ timestep_embed_kernel(const float* __restrict__ t_ptr, int t_stride, int rows, i
   }
 }
 
-// y[M, N] (+)= act_in(x)[M, K] . W[N, K]^T + b     for tiny M (time-embedding MLPs, per-resnet temb projections)
+// y[M, N] (+)= act_in(x)[M, K] . W[N, K]^T + b     for tiny M (time-embedding MLPs, per-resnet temb projections, embedding producers)
+// act_in (argument silu_in): 0 identity, 1 SiLU, 2 GELU(erf)
 // one warp per output column; x staged in smem in 16-row slabs; W rows streamed with 16-byte loads.
 __global__ void __launch_bounds__(256)
 skinny_linear_kernel(const uint16_t* __restrict__ x, long long ldx, const uint16_t* __restrict__ w, const uint16_t* __restrict__ bias,
-                     uint16_t* __restrict__ y, long long ldy, int M, int N, int K, int silu_in, int accumulate, int bf) {
-  extern __shared__ uint16_t xs[];               // [16][K]
+                     uint16_t* __restrict__ y, long long ldy, int M, int N, int K, int silu_in, int accumulate, int bf, int slab) {
+  extern __shared__ uint16_t xs[];               // [slab][K], slab <= 16
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col = blockIdx.x * (blockDim.x >> 5) + warp;
-  for (int m0 = 0; m0 < M; m0 += 16) {
-    const int mrows = min(16, M - m0);
+  for (int m0 = 0; m0 < M; m0 += slab) {
+    const int mrows = min(slab, M - m0);
     __syncthreads();
     for (int i = threadIdx.x; i < mrows * K; i += blockDim.x) {
       const int r = i / K, k = i % K;
       float v = load16(x, (size_t)(m0 + r) * ldx + k, bf);
-      if (silu_in) v = silu_f(v);
+      if (silu_in == 1) v = silu_f(v);
+      else if (silu_in == 2) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));   // exact-erf GELU (nn.GELU default)
       store16(xs, (size_t)r * K + k, v, bf);
     }
     __syncthreads();

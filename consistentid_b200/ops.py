@@ -154,9 +154,25 @@ def timestep_embed(t_dev, t_stride, rows, dim, out, ld, col0=0):
     return out
 
 
-def skinny_linear(x, w, bias, out, M, N, K, silu_in=False, accumulate=False):
-    call("cid_skinny_linear", _p(x), x.stride(0), _p(w), _p(bias), _p(out), out.stride(0), M, N, K, 1 if silu_in else 0,
+def skinny_linear(x, w, bias, out, M, N, K, silu_in=False, accumulate=False, act_in=None):
+    """out[M,N] (+)= act(x) @ w.T + bias; act_in: None -> SiLU if silu_in else identity; "silu" | "gelu" | "none"."""
+    act = {None: 1 if silu_in else 0, "none": 0, "silu": 1, "gelu": 2}[act_in]
+    call("cid_skinny_linear", _p(x), x.stride(0), _p(w), _p(bias), _p(out), out.stride(0), M, N, K, act,
          1 if accumulate else 0, _dt(x), _stream())
+    return out
+
+
+def layernorm_rows(x, gamma, beta, out, rows, C, eps=1e-5, rows_per_group=None, x_group_rows=None, x_row0=0, y_group_rows=None, y_row0=0):
+    """LayerNorm over ``rows`` logical rows of width C with the grouped row mapping of cid_layernorm_rows (x, out: 2-D row views)."""
+    rpg = rows if rows_per_group is None else rows_per_group
+    call("cid_layernorm_rows", _p(x), x.stride(0), rpg if x_group_rows is None else x_group_rows, x_row0, _p(gamma), _p(beta), _p(out),
+         out.stride(0), rpg if y_group_rows is None else y_group_rows, y_row0, rows, max(rpg, 1), C, float(eps), _dt(x), _stream())
+    return out
+
+
+def perceiver_attn(q, kv, out, B, L, n_kv, heads, dim_head=64):
+    """q [B*L, heads*64], kv [B*n_kv, 2*heads*64] (K | V), out [B*L, heads*64] (functions.py:446-453)."""
+    call("cid_perceiver_attn", _p(q), q.stride(0), _p(kv), kv.stride(0), _p(out), out.stride(0), B, L, n_kv, heads, dim_head, _dt(q), _stream())
     return out
 
 

@@ -74,7 +74,8 @@ int cid_add_inplace(void* y, const void* x, long long n_elems, int dtype, void* 
 
 /* diffusers get_timestep_embedding(flip_sin_to_cos=True, freq_shift=0); t read from device memory. */
 int cid_timestep_embed(const float* t_dev, int t_stride, int rows, int dim, void* out, long long ld, int col0, int dtype, void* stream);
-/* y[M,N] (+)= act(x)[M,K] . W[N,K]^T + b for M <= 64 (time_embedding, add_embedding, all time_emb_proj at once). */
+/* y[M,N] (+)= act(x)[M,K] . W[N,K]^T + b for small M (time_embedding, add_embedding, all time_emb_proj at once; the latent-row linears of the
+ * embedding producers).  silu_in selects act: 0 identity, 1 SiLU, 2 GELU(erf). */
 int cid_skinny_linear(const void* x, long long ldx, const void* W, const void* bias, void* y, long long ldy, int M, int N,
                       int K, int silu_in, int accumulate, int dtype, void* stream);
 
@@ -94,6 +95,18 @@ int cid_silu_inplace(void* y, long long n_elems, int dtype, void* stream);
  * x = (1-m) * (ca*image_latents + cn*noise) + m*x with {ca,cn} = blend_table[*step_dev] */
 int cid_inpaint_blend(float* x, void* x16, const float* image_latents, const float* noise, const float* mask, int B, int HW,
                       const float* blend_table, const int* step_dev, int dtype, void* stream);
+
+/* ---- embedding producers: the modules that write encoder_hidden_states = [77 fused text rows | 4 id rows] ---- */
+/* LayerNorm with grouped row mapping: logical row r = g*rows_per_group + i reads x row (g*x_group_rows + x_row0 + i) (pitch ldx) and writes
+ * y row (g*y_group_rows + y_row0 + i) (pitch ldy): norm1(x) / norm2(latents) of PerceiverAttention land directly in the concatenated
+ * key/value input (functions.py:434-444); also MLP.layernorm / FuseModule.layer_norm (attention.py:21,54) and FeedForward[0]. */
+int cid_layernorm_rows(const void* x, long long ldx, long long x_group_rows, long long x_row0, const void* gamma, const void* beta, void* y,
+                       long long ldy, long long y_group_rows, long long y_row0, long long rows, long long rows_per_group, int C, float eps,
+                       int dtype, void* stream);
+/* PerceiverAttention core (functions.py:446-453): per (sample, head, latent) softmax_fp32((q*s)(k*s)^T) v with s = dim_head^-1/4, dim_head 64.
+ * q [B*L, ldq]; kv [B*n_kv, ldkv] = to_kv output (K columns [0,heads*64), V columns [heads*64, 2*heads*64)); out [B*L, ldo]. */
+int cid_perceiver_attn(const void* q, long long ldq, const void* kv, long long ldkv, void* out, long long ldo, int B, int L, int n_kv, int heads,
+                       int dim_head, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -269,6 +269,49 @@ def check_skinny(M=16, N=1280, K=320, dtype=torch.float16, silu_in=True, seed=0)
     return _report(f"skinny M{M} N{N} K{K} silu{int(silu_in)}", out, ref, 5e-3)
 
 
+def check_skinny_gelu(M=5, N=768, K=3072, dtype=torch.float16, seed=0):
+    """FeedForward second linear of the perceiver stacks: y += gelu(x) @ W^T (functions.py:389-397)."""
+    ops = _ops()
+    x = _rand((M, K), dtype, seed)
+    w = _rand((N, K), dtype, seed + 1, K ** -0.5)
+    out = _rand((M, N), dtype, seed + 3)
+    prev = out.clone()
+    ops.skinny_linear(x, w, None, out, M, N, K, act_in="gelu", accumulate=True)
+    torch.cuda.synchronize()
+    ref = F.gelu(x.float()).to(dtype).float() @ w.float().T + prev.float()
+    return _report(f"skinny gelu M{M} N{N} K{K}", out, ref, 5e-3)
+
+
+def check_layernorm_rows(B=3, n=17, L=4, C=128, dtype=torch.float16, seed=0):
+    """LN1(x) and LN2(latents) written straight into the concatenated [B, n+L, C] key/value input (functions.py:434-444)."""
+    ops = _ops()
+    x, lat = _rand((B * n, C), dtype, seed), _rand((B * L, C), dtype, seed + 1)
+    g1, b1, g2, b2 = (_rand((C,), dtype, seed + 2 + i) for i in range(4))
+    kv_in = torch.zeros((B * (n + L), C), dtype=dtype, device=DEV)
+    ops.layernorm_rows(x, g1, b1, kv_in, B * n, C, rows_per_group=n, y_group_rows=n + L, y_row0=0)
+    ops.layernorm_rows(lat, g2, b2, kv_in, B * L, C, rows_per_group=L, y_group_rows=n + L, y_row0=n)
+    torch.cuda.synchronize()
+    ref = torch.cat([F.layer_norm(x.float().view(B, n, C), (C,), g1.float(), b1.float()),
+                     F.layer_norm(lat.float().view(B, L, C), (C,), g2.float(), b2.float())], dim=1).reshape(-1, C)
+    return _report(f"layernorm_rows B{B} n{n} L{L} C{C}", kv_in, ref, 4e-3)
+
+
+def check_perceiver_attn(B=2, L=4, n_kv=261, heads=3, dtype=torch.float16, seed=0):
+    ops = _ops()
+    inner = heads * 64
+    q = _rand((B * L, inner), dtype, seed)
+    kv = _rand((B * n_kv, 2 * inner), dtype, seed + 1)
+    out = torch.empty((B * L, inner), dtype=dtype, device=DEV)
+    ops.perceiver_attn(q, kv, out, B, L, n_kv, heads)
+    torch.cuda.synchronize()
+    split = lambda t, n: t.float().view(B, n, heads, 64).transpose(1, 2)
+    k, v = kv[:, :inner], kv[:, inner:]
+    s = 64 ** -0.25
+    w = torch.softmax((split(q, L) * s) @ (split(k, n_kv) * s).transpose(-1, -2), dim=-1)
+    ref = (w @ split(v, n_kv)).transpose(1, 2).reshape(B * L, inner)
+    return _report(f"perceiver_attn B{B} L{L} n{n_kv} h{heads}", out, ref, 1e-2 if dtype == torch.float16 else 2.5e-2)
+
+
 def check_cfg_step(dtype=torch.float16, seed=0):
     ops = _ops()
     B, HW, CP = 3, 64, 64
@@ -350,6 +393,12 @@ CHECKS = {
     "skinny": (check_skinny, dict(M=16, N=1280, K=320)),
     "skinny_m40": (check_skinny, dict(M=40, N=333, K=2816, silu_in=False)),
     "cfg_step": (check_cfg_step, {}),
+    "skinny_gelu": (check_skinny_gelu, dict(M=5, N=768, K=3072)),
+    "skinny_gelu_k8192": (check_skinny_gelu, dict(M=20, N=256, K=8192, dtype=B16)),
+    "ln_rows": (check_layernorm_rows, dict(B=3, n=17, L=4, C=128)),
+    "ln_rows_4096": (check_layernorm_rows, dict(B=1, n=5, L=1, C=4096, dtype=B16)),
+    "perceiver_attn": (check_perceiver_attn, dict(B=2, L=4, n_kv=261, heads=3)),
+    "perceiver_attn_1": (check_perceiver_attn, dict(B=5, L=1, n_kv=258, heads=16, dtype=B16)),
 }
 
 
