@@ -6,6 +6,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <mutex>
+#include <utility>
 
 #include <cudaTypedefs.h>
 
@@ -35,6 +36,23 @@ int fail(int code, const char* fmt, ...) {
     cudaError_t e__ = cudaGetLastError();                                                        \
     if (e__ != cudaSuccess) return fail(CID_ERR_CUDA, "%s launch: %s", name, cudaGetErrorString(e__)); \
   } while (0)
+
+// Programmatic dependent launch (see common.cuh): kernels that call griddep_wait() before touching global memory are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization so their prologue overlaps the predecessor's tail.  CID_PDL=0 disables it.
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("CID_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);   // error picked up by CID_CHECK_LAUNCH
+}
 
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 std::once_flag g_encode_once;
@@ -129,7 +147,7 @@ int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap
   const int n_tiles = (g.N + BN - 1) / BN;
   const int total = n_tiles * m_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc2_kernel<BN, STAGES><<<grid, GEMM2_THREADS, SM::TOTAL, st>>>(a1, a2, b, g, n_tiles, total);
+  launch_pdl(gemm_tc2_kernel<BN, STAGES>, dim3(grid), dim3(GEMM2_THREADS), SM::TOTAL, st, a1, a2, b, g, n_tiles, total);
   CID_CHECK_LAUNCH("gemm_tc2_kernel");
   return 0;
 }
@@ -282,7 +300,7 @@ int launch_attn_self3(const CUtensorMap& q, const CUtensorMap& k, const CUtensor
   static bool configured = false;
   if (!configured) { int rc = set_smem(attn_self3_kernel<D_PAD>, C::TOTAL, "attn_self3_kernel"); if (rc) return rc; configured = true; }
   dim3 grid((a.Nq + 127) / 128, a.H, a.B);
-  attn_self3_kernel<D_PAD><<<grid, ATTN_THREADS, C::TOTAL, st>>>(q, k, v, a);
+  launch_pdl(attn_self3_kernel<D_PAD>, dim3(grid), dim3(ATTN_THREADS), C::TOTAL, st, q, k, v, a);
   CID_CHECK_LAUNCH("attn_self3_kernel");
   return 0;
 }
@@ -292,7 +310,7 @@ int launch_attn_cross(const CUtensorMap& q, const CUtensorMap& k, const CUtensor
   static bool configured = false;
   if (!configured) { int rc = set_smem(attn_cross_kernel<D_PAD>, C::TOTAL, "attn_cross_kernel"); if (rc) return rc; configured = true; }
   dim3 grid((a.Nq + 127) / 128, a.H, a.B);
-  attn_cross_kernel<D_PAD><<<grid, 128, C::TOTAL, st>>>(q, k, v, a);
+  launch_pdl(attn_cross_kernel<D_PAD>, dim3(grid), dim3(128), C::TOTAL, st, q, k, v, a);
   CID_CHECK_LAUNCH("attn_cross_kernel");
   return 0;
 }
@@ -511,7 +529,7 @@ int cid_gn_stats(const void* x1, int C1, const void* x2, int C2, int NB, int HW,
   int slabs = (148 * 8) / (NB * zchunks); if (slabs < 1) slabs = 1;
   const int tpp = 256 / (V < 256 ? V : 256);
   const int max_slabs = (HW + tpp - 1) / tpp; if (slabs > max_slabs) slabs = max_slabs;
-  gn_stats_kernel<<<dim3(slabs, NB, zchunks), 256, 0, st>>>((const uint16_t*)x1, C1, (const uint16_t*)x2, C2, HW, groups, sums, dtype == CID_BF16);
+  launch_pdl(gn_stats_kernel, dim3(slabs, NB, zchunks), dim3(256), 0, st, (const uint16_t*)x1, C1, (const uint16_t*)x2, C2, HW, groups, sums, int(dtype == CID_BF16));
   CID_CHECK_LAUNCH("gn_stats_kernel");
   return 0;
 }
@@ -523,9 +541,9 @@ int cid_gn_apply(const void* x1, int C1, const void* x2, int C2, int NB, int HW,
   if (C > 4096) return fail(CID_ERR_UNSUPPORTED, "cid_gn_apply: C=%d > 4096", C);
   int slabs = grid_for((long long)HW * (C / 8), 256) / NB;
   if (slabs < 1) slabs = 1;
-  gn_apply_kernel<<<dim3(slabs, NB), 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      (const uint16_t*)x1, C1, (const uint16_t*)x2, C2, HW, groups, sums, (const uint16_t*)gamma, (const uint16_t*)beta, eps, silu,
-      (uint16_t*)y, total, dtype == CID_BF16);
+  launch_pdl(gn_apply_kernel, dim3(slabs, NB), dim3(256), 2 * C * sizeof(float), static_cast<cudaStream_t>(stream),
+             (const uint16_t*)x1, C1, (const uint16_t*)x2, C2, HW, groups, sums, (const uint16_t*)gamma, (const uint16_t*)beta, eps, silu,
+             (uint16_t*)y, total, int(dtype == CID_BF16));
   CID_CHECK_LAUNCH("gn_apply_kernel");
   return 0;
 }
@@ -535,7 +553,7 @@ int cid_layernorm(const void* x, const void* gamma, const void* beta, void* y, l
   const unsigned grid = (unsigned)((rows + rows_per_block - 1) / rows_per_block);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int maxv = (C / 8 + 31) / 32;
-#define CID_LN(MV) layernorm_kernel<MV><<<grid, 256, 0, st>>>((const uint16_t*)x, (const uint16_t*)gamma, (const uint16_t*)beta, (uint16_t*)y, rows, C, eps, dtype == CID_BF16)
+#define CID_LN(MV) launch_pdl(layernorm_kernel<MV>, dim3(grid), dim3(256), 0, st, (const uint16_t*)x, (const uint16_t*)gamma, (const uint16_t*)beta, (uint16_t*)y, rows, C, eps, int(dtype == CID_BF16))
   if (maxv <= 1) CID_LN(1); else if (maxv <= 2) CID_LN(2); else if (maxv <= 3) CID_LN(3); else if (maxv <= 5) CID_LN(5); else CID_LN(8);
 #undef CID_LN
   CID_CHECK_LAUNCH("layernorm_kernel");

@@ -329,6 +329,8 @@ attn_cross_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_S = tmem, tmem_Ot = tmem, tmem_Oi = tmem + D_PAD;      // O_* overwrite S after the softmax has read it
+  griddep_launch_dependents();     // PDL: the prologue above overlaps the predecessor's tail
+  griddep_wait();
 
   if (warp == 0 && lane == 0) {
     mbar_expect_tx(bar_ld, C::Q_BYTES + C::K_BYTES + C::V_BYTES);

@@ -64,6 +64,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // generic-proxy smem writes -> visible to the async proxy (TMA / UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ------------------------------------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is still
+// draining: griddep_wait() blocks until every prerequisite grid has completed and its memory is visible (must precede the first access
+// to data a predecessor wrote, or to a buffer a predecessor still reads); griddep_launch_dependents() lets the successor's CTAs be
+// scheduled as soon as this grid's CTAs have all started, so its prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps
+// this grid's tail.  Both are no-ops for a normal launch.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

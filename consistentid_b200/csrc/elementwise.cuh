@@ -24,6 +24,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], int bf) {
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const uint16_t* __restrict__ x1, int C1, const uint16_t* __restrict__ x2, int C2, int HW, int groups,
                 float* __restrict__ sums, int bf) {
+  griddep_launch_dependents();     // PDL (no-op for a normal launch)
+  griddep_wait();
   __shared__ float sh[2 * 2048];                 // per-channel partial sums of this block's channel chunk
   const int C = C1 + C2, V = C / 8;              // 8-channel vectors per pixel
   const int n = blockIdx.y;
@@ -82,6 +84,8 @@ __global__ void __launch_bounds__(256)
 gn_apply_kernel(const uint16_t* __restrict__ x1, int C1, const uint16_t* __restrict__ x2, int C2, int HW, int groups,
                 const float* __restrict__ sums, const uint16_t* __restrict__ gamma, const uint16_t* __restrict__ beta,
                 float eps, int do_silu, uint16_t* __restrict__ y, long long total_vec, int bf) {
+  griddep_launch_dependents();     // PDL (no-op for a normal launch)
+  griddep_wait();
   // grid (slabs, NB): a block serves ONE sample, so the per-channel affine (scale = rstd*gamma, shift = beta - mean*scale)
   // is built once in smem and the streaming loop is one FMA (+ SiLU) per element.
   extern __shared__ float aff[];                 // [2 * C]
@@ -130,6 +134,8 @@ template <int MAXV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ gamma, const uint16_t* __restrict__ beta,
                  uint16_t* __restrict__ y, long long rows, int C, float eps, int bf) {
+  griddep_launch_dependents();     // PDL (no-op for a normal launch)
+  griddep_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;

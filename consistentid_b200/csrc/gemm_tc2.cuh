@@ -71,6 +71,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // prologue above touched only shared memory / TMEM / descriptors: it may overlap the predecessor's tail (PDL)
+  griddep_launch_dependents();
+  griddep_wait();
 
   auto tile_origin = [&](int mt, int& tn0, int& ty0, int& tx0) {
     const int tx = mt % g.tiles_x;
