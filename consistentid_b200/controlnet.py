@@ -105,6 +105,7 @@ class B200ControlNet(B200UNet):
         NB, H, W = self._plan
         spec, P, buf = self.spec, self.params, self._buf
         kv = self._kv[key]
+        self._gn_k = 0
         cond, cb, ch, cw = self._cond
         assert (cb, ch, cw) == (NB, H, W), ("control image does not match the latent batch/resolution", (cb, ch, cw), (NB, H, W))
         emb, temb_all = self._time_embedding(key)

@@ -135,6 +135,14 @@ int gemm_version() {
   return g_gemm_version;
 }
 
+// Split-K workspace (caller-provided through cid_set_workspace; the library never allocates): [4 KB counters | fp32 partials]
+void* g_ws = nullptr;
+size_t g_ws_bytes = 0;
+constexpr size_t WS_COUNTER_BYTES = 4096;
+int env_int(const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; }
+int splitk_min_kb() { static const int v = env_int("CID_GEMM_SPLIT_MIN_KB", 16); return v < 1 ? 1 : v; }     // k-blocks per split unit
+int splitk_max() { static const int v = env_int("CID_GEMM_SPLITK", 8); return v; }                            // 0/1 disables
+
 template <int BN, int STAGES>
 int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
   using SM = Gemm2Smem<BN, STAGES>;
@@ -146,8 +154,27 @@ int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap
   }
   const int n_tiles = (g.N + BN - 1) / BN;
   const int total = n_tiles * m_tiles;
-  const int grid = total < num_sms() ? total : num_sms();
-  launch_pdl(gemm_tc2_kernel<BN, STAGES>, dim3(grid), dim3(GEMM2_THREADS), SM::TOTAL, st, a1, a2, b, g, n_tiles, total);
+  const int G = num_sms();
+  GemmSched sched{};
+  int grid;
+  if (total >= G) { grid = G; sched.full_iters = total / G; sched.tail_tiles = total % G; }
+  else { grid = total; sched.full_iters = 0; sched.tail_tiles = total; }
+  sched.ksplit = 1;
+  // tail balancing: cut each tail tile into K-ranges so that (almost) every SM gets a share (see gemm_tc2.cuh)
+  if (sched.tail_tiles > 0 && g_ws != nullptr && splitk_max() > 1) {
+    const int num_kb = g.taps * (g.kblocks_a1 + g.kblocks_a2);
+    int sp = G / sched.tail_tiles;
+    if (sp > num_kb / splitk_min_kb()) sp = num_kb / splitk_min_kb();
+    if (sp > splitk_max()) sp = splitk_max();
+    const size_t need = WS_COUNTER_BYTES + (size_t)sched.tail_tiles * sp * GEMM_BM * BN * sizeof(float);
+    if (sp >= 2 && sched.tail_tiles * sizeof(int) <= WS_COUNTER_BYTES && need <= g_ws_bytes) {
+      sched.ksplit = sp;
+      sched.counters = reinterpret_cast<int*>(g_ws);
+      sched.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(g_ws) + WS_COUNTER_BYTES);
+      if (sched.tail_tiles * sp > grid) grid = sched.tail_tiles * sp;
+    }
+  }
+  launch_pdl(gemm_tc2_kernel<BN, STAGES>, dim3(grid), dim3(GEMM2_THREADS), SM::TOTAL, st, a1, a2, b, g, n_tiles, sched);
   CID_CHECK_LAUNCH("gemm_tc2_kernel");
   return 0;
 }
@@ -518,12 +545,14 @@ int cid_pack_cross_kv(const void* k_text, const void* v_text, const void* k_ip, 
   return 0;
 }
 
-int cid_gn_stats(const void* x1, int C1, const void* x2, int C2, int NB, int HW, int groups, float* sums, int dtype, void* stream) {
+int cid_gn_stats(const void* x1, int C1, const void* x2, int C2, int NB, int HW, int groups, float* sums, int zero_sums, int dtype, void* stream) {
   const int C = C1 + C2;
   if (!x1 || !sums || C1 % 8 || C2 % 8 || C % groups || (C2 > 0 && !x2)) return fail(CID_ERR_ARG, "cid_gn_stats: bad arguments (C1=%d C2=%d groups=%d)", C1, C2, groups);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * NB * groups, st);
-  if (e != cudaSuccess) return fail(CID_ERR_CUDA, "cid_gn_stats memset: %s", cudaGetErrorString(e));
+  if (zero_sums) {
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * NB * groups, st);
+    if (e != cudaSuccess) return fail(CID_ERR_CUDA, "cid_gn_stats memset: %s", cudaGetErrorString(e));
+  }
   const int V = C / 8;
   const int zchunks = (V + 255) / 256;
   int slabs = (148 * 8) / (NB * zchunks); if (slabs < 1) slabs = 1;
@@ -534,16 +563,15 @@ int cid_gn_stats(const void* x1, int C1, const void* x2, int C2, int NB, int HW,
   return 0;
 }
 int cid_gn_apply(const void* x1, int C1, const void* x2, int C2, int NB, int HW, int groups, const float* sums, const void* gamma,
-                 const void* beta, float eps, int silu, void* y, int dtype, void* stream) {
+                 const void* beta, float eps, int silu, void* y, float* zero_next, int dtype, void* stream) {
   const int C = C1 + C2;
   if (!x1 || !sums || !gamma || !beta || !y || C1 % 8 || C2 % 8 || C % groups) return fail(CID_ERR_ARG, "cid_gn_apply: bad arguments");
-  const long long total = (long long)NB * HW * (C / 8);
   if (C > 4096) return fail(CID_ERR_UNSUPPORTED, "cid_gn_apply: C=%d > 4096", C);
   int slabs = grid_for((long long)HW * (C / 8), 256) / NB;
   if (slabs < 1) slabs = 1;
   launch_pdl(gn_apply_kernel, dim3(slabs, NB), dim3(256), 2 * C * sizeof(float), static_cast<cudaStream_t>(stream),
              (const uint16_t*)x1, C1, (const uint16_t*)x2, C2, HW, groups, sums, (const uint16_t*)gamma, (const uint16_t*)beta, eps, silu,
-             (uint16_t*)y, total, int(dtype == CID_BF16));
+             (uint16_t*)y, zero_next, int(dtype == CID_BF16));
   CID_CHECK_LAUNCH("gn_apply_kernel");
   return 0;
 }
@@ -644,6 +672,13 @@ int cid_advance_step(int* step_dev, float* t_dev, const float* ts_table, int n, 
   if (!step_dev || !t_dev || !ts_table || n <= 0) return fail(CID_ERR_ARG, "cid_advance_step: bad arguments");
   advance_step_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(step_dev, t_dev, ts_table, n);
   CID_CHECK_LAUNCH("advance_step_kernel");
+  return 0;
+}
+
+int cid_set_workspace(void* workspace, unsigned long long bytes) {
+  if (workspace == nullptr || bytes < WS_COUNTER_BYTES) { g_ws = nullptr; g_ws_bytes = 0; return 0; }
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) return fail(CID_ERR_ARG, "cid_set_workspace: pointer must be 256-byte aligned");
+  g_ws = workspace; g_ws_bytes = (size_t)bytes;
   return 0;
 }
 

@@ -329,8 +329,7 @@ attn_cross_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_S = tmem, tmem_Ot = tmem, tmem_Oi = tmem + D_PAD;      // O_* overwrite S after the softmax has read it
-  griddep_launch_dependents();     // PDL: the prologue above overlaps the predecessor's tail
-  griddep_wait();
+  griddep_wait();                  // PDL: the prologue above overlaps the predecessor's tail
 
   if (warp == 0 && lane == 0) {
     mbar_expect_tx(bar_ld, C::Q_BYTES + C::K_BYTES + C::V_BYTES);
@@ -339,6 +338,7 @@ attn_cross_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tma_load_4d(sbase + C::OFF_K + ch * C::K_CHUNK, &tmK, bar_ld, ch * 64, 0, h, b);
     }
     for (int kc = 0; kc < 2; ++kc) tma_load_3d(sbase + C::OFF_V + kc * C::V_CHUNK, &tmVt, bar_ld, kc * 64, 0, b * a.H + h);
+    griddep_launch_dependents();
     mbar_wait(bar_ld, 0);
     tc_fence_after();
     const uint32_t idesc_s = make_idesc(128, C::KROWS, a.is_bf16);

@@ -74,8 +74,7 @@ attn_self3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_S = tmem, tmem_O = tmem + 128, tmem_L = tmem + 128 + D_PAD;
-  griddep_launch_dependents();     // PDL: the prologue above overlaps the predecessor's tail
-  griddep_wait();
+  griddep_wait();                  // PDL: the prologue above overlaps the predecessor's tail
 
   if (warp == 0) {
     // ============================================================ TMA producer
@@ -99,6 +98,7 @@ attn_self3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      griddep_launch_dependents();
     }
     __syncwarp();
   } else if (warp == 1) {

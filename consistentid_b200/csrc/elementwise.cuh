@@ -24,8 +24,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], int bf) {
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const uint16_t* __restrict__ x1, int C1, const uint16_t* __restrict__ x2, int C2, int HW, int groups,
                 float* __restrict__ sums, int bf) {
-  griddep_launch_dependents();     // PDL (no-op for a normal launch)
-  griddep_wait();
+  griddep_wait();                  // PDL (no-op for a normal launch)
   __shared__ float sh[2 * 2048];                 // per-channel partial sums of this block's channel chunk
   const int C = C1 + C2, V = C / 8;              // 8-channel vectors per pixel
   const int n = blockIdx.y;
@@ -83,9 +82,8 @@ gn_stats_kernel(const uint16_t* __restrict__ x1, int C1, const uint16_t* __restr
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const uint16_t* __restrict__ x1, int C1, const uint16_t* __restrict__ x2, int C2, int HW, int groups,
                 const float* __restrict__ sums, const uint16_t* __restrict__ gamma, const uint16_t* __restrict__ beta,
-                float eps, int do_silu, uint16_t* __restrict__ y, long long total_vec, int bf) {
-  griddep_launch_dependents();     // PDL (no-op for a normal launch)
-  griddep_wait();
+                float eps, int do_silu, uint16_t* __restrict__ y, float* __restrict__ zero_next, int bf) {
+  griddep_wait();                  // PDL (no-op for a normal launch)
   // grid (slabs, NB): a block serves ONE sample, so the per-channel affine (scale = rstd*gamma, shift = beta - mean*scale)
   // is built once in smem and the streaming loop is one FMA (+ SiLU) per element.
   extern __shared__ float aff[];                 // [2 * C]
@@ -101,6 +99,9 @@ gn_apply_kernel(const uint16_t* __restrict__ x1, int C1, const uint16_t* __restr
     aff[c] = sc;
     aff[C + c] = load16(beta, c, bf) - mean * sc;
   }
+  // the statistics buffer the NEXT GroupNorm accumulates into (its last reader finished before this grid started)
+  if (zero_next != nullptr && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) zero_next[(size_t)n * groups * 2 + i] = 0.f;
   __syncthreads();
   const long long per_sample = (long long)HW * V;
   const uint16_t* x1n = x1 + (size_t)n * HW * C1;
@@ -124,7 +125,6 @@ gn_apply_kernel(const uint16_t* __restrict__ x1, int C1, const uint16_t* __restr
     }
     *reinterpret_cast<uint4*>(yn + pix * C + c0) = pack8(f, bf);
   }
-  (void)total_vec;
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
@@ -134,8 +134,7 @@ template <int MAXV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ gamma, const uint16_t* __restrict__ beta,
                  uint16_t* __restrict__ y, long long rows, int C, float eps, int bf) {
-  griddep_launch_dependents();     // PDL (no-op for a normal launch)
-  griddep_wait();
+  griddep_wait();                  // PDL (no-op for a normal launch)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;

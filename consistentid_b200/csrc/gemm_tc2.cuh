@@ -8,6 +8,13 @@
 //   warps 2-9   epilogue: two warps per TMEM lane quarter, each draining half of the tile's columns in 16-column
 //               tcgen05.ld chunks; residual rows are prefetched into registers BEFORE waiting for the accumulator and the
 //               bias slice of the tile is staged once in smem, so no global-load latency sits between TMEM and the stores
+//
+// Tail balancing (split-K): a launch of T tiles on G CTAs runs floor(T/G) whole-tile rounds; the remaining T mod G tiles would keep
+// G - (T mod G) SMs idle for a full tile time (M=4096/1024 levels of SD1.5: 160 or 40 tiles, SDXL N=1280 GEMMs: 320 tiles = 2.16
+// waves).  When the K loop is long enough each tail tile is cut into `ksplit` K-ranges handled by different CTAs: every unit publishes
+// its fp32 partial accumulator to a workspace ([chunk][row][16] floats, coalesced), bumps the tile's arrival counter, and the LAST
+// arriver adds the other partials into its own TMEM accumulator (tcgen05.ld -> add -> tcgen05.st) and runs the normal fused epilogue.
+// No unit ever waits for another one, so there is no ordering requirement between CTAs.
 #pragma once
 #include <type_traits>
 #include "elementwise.cuh"
@@ -25,15 +32,34 @@ struct Gemm2Smem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int BIAS_OFF = BAR_OFF + 256;             // 2 x BN floats
-  static constexpr int TOTAL = BIAS_OFF + 2 * BN * 4 + 1024;
+  static constexpr int FLAG_OFF = BIAS_OFF + 2 * BN * 4;     // split-K "last arriver" flag
+  static constexpr int TOTAL = FLAG_OFF + 16 + 1024;
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Work list of one CTA: `full_iters` whole tiles (tile = blockIdx.x + i*gridDim.x), then at most one tail item: a whole tail tile
+// (ksplit <= 1, blockIdx.x < tail_tiles) or K-range `split` of tail tile blockIdx.x / ksplit.
+struct GemmSched {
+  int full_iters, tail_tiles, ksplit;
+  float* ws;        // split-K partials: [tail tile][split][BN/16 chunks][128 rows][16] fp32
+  int* counters;    // [tail tile] arrival counters, zero between launches
+};
+struct GemmWork { int tile, kb0, kb1, split, tail_idx; };
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-                const __grid_constant__ CUtensorMap tmB, const GemmArgs g, const int n_tiles, const int total_tiles) {
+                const __grid_constant__ CUtensorMap tmB, const GemmArgs g, const int n_tiles, const GemmSched sched) {
   static_assert(BN % 32 == 0 || BN == 16, "column split");
   constexpr int ACC_STRIDE = 256;                              // TMEM column offset between the two accumulators
   using SM = Gemm2Smem<BN, STAGES>;
@@ -52,6 +78,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
   const int lane = lane_id();
   const int kb_per_tap = g.kblocks_a1 + g.kblocks_a2;
   const int num_kb = g.taps * kb_per_tap;
+  const int n_work = sched.full_iters + ((int)blockIdx.x < (sched.ksplit > 1 ? sched.tail_tiles * sched.ksplit : sched.tail_tiles) ? 1 : 0);
+  auto get_work = [&](int it) -> GemmWork {
+    if (it < sched.full_iters) return GemmWork{int(blockIdx.x) + it * int(gridDim.x), 0, num_kb, -1, 0};
+    const int base = sched.full_iters * int(gridDim.x);
+    if (sched.ksplit <= 1) return GemmWork{base + int(blockIdx.x), 0, num_kb, -1, 0};
+    const int t = int(blockIdx.x) / sched.ksplit, sp = int(blockIdx.x) - t * sched.ksplit;
+    return GemmWork{base + t, sp * num_kb / sched.ksplit, (sp + 1) * num_kb / sched.ksplit, sp, t};
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
@@ -72,7 +106,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // prologue above touched only shared memory / TMEM / descriptors: it may overlap the predecessor's tail (PDL)
-  griddep_launch_dependents();
   griddep_wait();
 
   auto tile_origin = [&](int mt, int& tn0, int& ty0, int& tx0) {
@@ -86,11 +119,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     if (lane == 0) {
       const uint32_t a_bytes = (g.a_mode == A_GEMM) ? uint32_t(SM::A_BYTES) : uint32_t(g.TW * g.TH * g.TN * 128);
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int it = 0; it < n_work; ++it) {
+        const GemmWork w = get_work(it);
+        const int tile = w.tile;
         const int nt = tile % n_tiles, mt = tile / n_tiles;
         int tn0 = 0, ty0 = 0, tx0 = 0;
         if (g.a_mode != A_GEMM) tile_origin(mt, tn0, ty0, tx0);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * SM::STAGE_BYTES;
           const uint32_t sb = sa + SM::A_BYTES;
@@ -113,31 +148,32 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
+      griddep_launch_dependents();   // all loads of this CTA are in flight: the successor's prologue may overlap the remaining MMAs + epilogue
     }
     __syncwarp();
   } else if (warp == 1) {
     // ================================================================ MMA issuer
     const uint32_t idesc = make_idesc(GEMM_BM, BN, g.is_bf16);
     int stage = 0; uint32_t phase = 0;
-    int it = 0;
     const uint32_t a_lo0 = desc_lo(smem_base);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int it = 0; it < n_work; ++it) {
+      const GemmWork w = get_work(it);
       const int ab = it & 1;
       const uint32_t aphase = uint32_t(it >> 1) & 1u;
       mbar_wait(acc_empty(ab), aphase ^ 1u);              // epilogue has drained this accumulator (first use: free)
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + ab * ACC_STRIDE;
       if (lane == 0) {                                     // one thread runs the whole issue loop (no per-k-block warp sync)
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + uint32_t(stage) * uint32_t(SM::STAGE_BYTES / 16);
           const uint32_t b_lo = a_lo + uint32_t(SM::A_BYTES / 16);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_ss(tmem_acc, desc_make(a_lo + k * 2), desc_make(b_lo + k * 2), idesc, (kb | k) ? 1u : 0u);
+            umma_ss(tmem_acc, desc_make(a_lo + k * 2), desc_make(b_lo + k * 2), idesc, ((kb - w.kb0) | k) ? 1u : 0u);
           umma_commit(empty_bar(stage));
-          if (kb == num_kb - 1) umma_commit(acc_full(ab));
+          if (kb == w.kb1 - 1) umma_commit(acc_full(ab));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -174,8 +210,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
       grow_ = ((long long)n * g.H + y) * g.W + x;
       return (dn < g.TN) && (n < g.NB) && (y < g.H) && (x < g.W);
     };
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    volatile int* last_flag = reinterpret_cast<volatile int*>(smem_gen + SM::FLAG_OFF);
+    for (int it = 0; it < n_work; ++it) {
+      const GemmWork w = get_work(it);
+      const int tile = w.tile;
       const int ab = it & 1;
       const uint32_t aphase = uint32_t(it >> 1) & 1u;
       const int nt = tile % n_tiles, mt = tile / n_tiles;
@@ -205,7 +243,73 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
       tc_fence_after();
       const uint32_t t_row = tmem_base + ab * ACC_STRIDE + (uint32_t(quarter * 32) << 16);
 
-      if (BN >= 32 && geglu) {
+      bool run_epilogue = true;
+      if (w.split >= 0) {
+        // ---- split-K tail unit: publish the partial accumulator; the last arriver of the tile folds the others in and finishes
+        constexpr int SLOT = GEMM_BM * BN;                                  // floats per partial
+        float* tile_ws = sched.ws + (size_t)w.tail_idx * sched.ksplit * SLOT;
+        float* mine = tile_ws + (size_t)w.split * SLOT;
+        const int nsets = geglu ? 2 : 1;                                    // GEGLU threads own a value chunk and the matching gate chunk
+        for (int set = 0; set < nsets; ++set) {
+#pragma unroll
+          for (int c = 0; c < MAXCH; ++c) {
+            const int ch = ch_beg + c;
+            if (ch < ch_end) {
+              const int colc = ch + set * (BN / 32);                          // 16-column chunk index inside the tile
+              uint32_t a[16];
+              tmem_ld_x16(t_row + colc * 16, a);
+              tmem_ld_wait();
+              float4* dst = reinterpret_cast<float4*>(mine + ((size_t)colc * GEMM_BM + r) * 16);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                dst[j] = make_float4(__uint_as_float(a[4 * j]), __uint_as_float(a[4 * j + 1]), __uint_as_float(a[4 * j + 2]), __uint_as_float(a[4 * j + 3]));
+            }
+          }
+        }
+        __threadfence();
+        epi_bar_sync();
+        if (et == 0) {
+          const int old = atomicAdd(sched.counters + w.tail_idx, 1);
+          const int last = (old == sched.ksplit - 1) ? 1 : 0;
+          if (last) sched.counters[w.tail_idx] = 0;                         // every unit of this tile has arrived: re-arm for the next launch
+          *last_flag = last;
+        }
+        epi_bar_sync();
+        run_epilogue = (*last_flag != 0);
+        if (run_epilogue) {
+          __threadfence();
+          for (int set = 0; set < nsets; ++set) {
+#pragma unroll
+            for (int c = 0; c < MAXCH; ++c) {
+              const int ch = ch_beg + c;
+              if (ch < ch_end) {
+                const int colc = ch + set * (BN / 32);
+                uint32_t a[16];
+                tmem_ld_x16(t_row + colc * 16, a);
+                tmem_ld_wait();
+                for (int sp = 0; sp < sched.ksplit; ++sp) {
+                  if (sp == w.split) continue;
+                  const float4* src = reinterpret_cast<const float4*>(tile_ws + (size_t)sp * SLOT + ((size_t)colc * GEMM_BM + r) * 16);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float4 p = __ldcg(src + j);
+                    a[4 * j] = __float_as_uint(__uint_as_float(a[4 * j]) + p.x);
+                    a[4 * j + 1] = __float_as_uint(__uint_as_float(a[4 * j + 1]) + p.y);
+                    a[4 * j + 2] = __float_as_uint(__uint_as_float(a[4 * j + 2]) + p.z);
+                    a[4 * j + 3] = __float_as_uint(__uint_as_float(a[4 * j + 3]) + p.w);
+                  }
+                }
+                tmem_st16(t_row + colc * 16, a);
+              }
+            }
+          }
+          tmem_st16_wait();
+        }
+      }
+
+      if (!run_epilogue) {
+        // partial published; nothing else to do for this unit
+      } else if (BN >= 32 && geglu) {
         constexpr int HALF = BN / 2;
         const int out_col0 = nt * HALF;
 #pragma unroll

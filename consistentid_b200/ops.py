@@ -25,6 +25,22 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---- GEMM tail-balancing workspace: one zero-filled buffer per process (one process per GPU), handed to the library once and kept alive
+_WORKSPACE = None
+WORKSPACE_BYTES = 24 << 20
+
+
+def ensure_workspace(device=None):
+    """Give libcidb200 its split-K scratch (cid_set_workspace).  Idempotent; called by the engines and by ``gemm``/``conv3x3``."""
+    global _WORKSPACE
+    if _WORKSPACE is None:
+        _WORKSPACE = torch.zeros(WORKSPACE_BYTES, dtype=torch.uint8, device=device or torch.device("cuda", torch.cuda.current_device()))
+        rc = lib._lib.cid_set_workspace(_WORKSPACE.data_ptr(), WORKSPACE_BYTES)
+        if rc != 0:
+            raise lib.CidError(f"cid_set_workspace failed ({rc}): {lib.last_error()}")
+    return _WORKSPACE
+
+
 # ---- optional per-launch profiling (bench.py roofline pass): each tensor-core launch bracketed by CUDA events on the
 # launching (= torch current) stream, with its algorithmic FLOPs / bytes
 _PROFILE = None
@@ -40,12 +56,12 @@ def profile_end():
     global _PROFILE
     rec, _PROFILE = _PROFILE, None
     torch.cuda.synchronize()
-    return [dict(kind=k, flops=f, bytes=b, ms=e0.elapsed_time(e1)) for k, f, b, e0, e1 in rec]
+    return [dict(kind=k, flops=f, bytes=b, ms=e0.elapsed_time(e1), shape=sh) for k, f, b, e0, e1, sh in rec]
 
 
 class _prof:
-    def __init__(self, kind, flops, nbytes):
-        self.kind, self.flops, self.nbytes = kind, flops, nbytes
+    def __init__(self, kind, flops, nbytes, shape=None):
+        self.kind, self.flops, self.nbytes, self.shape = kind, flops, nbytes, shape
 
     def __enter__(self):
         if _PROFILE is not None:
@@ -55,7 +71,7 @@ class _prof:
     def __exit__(self, *a):
         if _PROFILE is not None:
             self.e1.record()
-            _PROFILE.append((self.kind, self.flops, self.nbytes, self.e0, self.e1))
+            _PROFILE.append((self.kind, self.flops, self.nbytes, self.e0, self.e1, self.shape))
 
 
 def _chk(t, name):
@@ -73,7 +89,9 @@ def gemm(a, w, out, bias=None, residual=None, rowbias=None, rows_per_group=1, a2
     N = w.shape[0]
     assert w.shape[1] == K1 + K2 and w.is_contiguous()
     assert a.stride(1) == 1 and out.stride(1) == 1
-    with _prof("gemm", 2.0 * M * N * (K1 + K2), 2.0 * (M * (K1 + K2) + N * (K1 + K2) + M * N)):
+    if _WORKSPACE is None:
+        ensure_workspace(a.device)
+    with _prof("gemm", 2.0 * M * N * (K1 + K2), 2.0 * (M * (K1 + K2) + N * (K1 + K2) + M * N), (M, N, K1 + K2, epi)):
         call("cid_gemm", _p(a), a.stride(0), _p(a2), 0 if a2 is None else a2.stride(0), K1, K2, _p(w), _p(out), out.stride(0),
              M, N, _p(bias), _p(residual), 0 if residual is None else residual.stride(0), _p(rowbias), rows_per_group,
              0 if rowbias is None else rowbias.stride(0), epi, _p(vt), n_split, heads, hdim, ntok, float(out_scale), _dt(a), _stream())
@@ -84,7 +102,9 @@ def conv3x3(x, w, out, NB, H, W, Cin, Cout, bias=None, residual=None, rowbias=No
     """x: NHWC [NB,H,W,Cin] (or phase-split [NB,4,H,W,Cin] when stride2; H,W = output dims); w: [Cout, 9*Cin];
     out: [NB*H*W, >=Cout] rows."""
     M = NB * H * W
-    with _prof("conv3x3", 2.0 * M * Cout * 9 * Cin, 2.0 * (M * Cin * (4 if stride2 else 1) + 9 * Cin * Cout + M * Cout)):
+    if _WORKSPACE is None:
+        ensure_workspace(x.device)
+    with _prof("conv3x3", 2.0 * M * Cout * 9 * Cin, 2.0 * (M * Cin * (4 if stride2 else 1) + 9 * Cin * Cout + M * Cout), (M, Cout, 9 * Cin, 0)):
         call("cid_conv3x3", _p(x), _p(w), _p(out), out.stride(0), NB, H, W, Cin, Cout, 1 if stride2 else 0, _p(bias), _p(residual),
              0 if residual is None else residual.stride(0), _p(rowbias), 0 if rowbias is None else rowbias.stride(0),
              float(out_scale), _dt(x), _stream())
@@ -109,13 +129,13 @@ def pack_cross_kv(k_text, v_text, k_ip, v_ip, k_cat, vt_cat, B, C, heads, n_text
     call("cid_pack_cross_kv", _p(k_text), _p(v_text), _p(k_ip), _p(v_ip), _p(k_cat), _p(vt_cat), B, C, heads, n_text, n_ip, _stream())
 
 
-def gn_stats(x1, C1, x2, C2, NB, HW, groups, sums):
-    call("cid_gn_stats", _p(x1), C1, _p(x2), C2, NB, HW, groups, _p(sums), _dt(x1), _stream())
+def gn_stats(x1, C1, x2, C2, NB, HW, groups, sums, zero_sums=True):
+    call("cid_gn_stats", _p(x1), C1, _p(x2), C2, NB, HW, groups, _p(sums), 1 if zero_sums else 0, _dt(x1), _stream())
 
 
-def gn_apply(x1, C1, x2, C2, NB, HW, groups, sums, gamma, beta, eps, silu, out):
+def gn_apply(x1, C1, x2, C2, NB, HW, groups, sums, gamma, beta, eps, silu, out, zero_next=None):
     call("cid_gn_apply", _p(x1), C1, _p(x2), C2, NB, HW, groups, _p(sums), _p(gamma), _p(beta), float(eps), 1 if silu else 0,
-         _p(out), _dt(x1), _stream())
+         _p(out), _p(zero_next), _dt(x1), _stream())
     return out
 
 

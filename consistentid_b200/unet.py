@@ -163,6 +163,7 @@ class B200UNet:
         self._active_key = None
         self._slots, self._ident, self._auto_next = {}, {}, 0
         self._graphs = {}
+        self._gn_k = 0
         self._procs = {n: _EngineProcessor(self, n) for n in attn_processor_names(spec)}
 
     # ------------------------------------------------------------------ diffusers-facing surface
@@ -307,9 +308,13 @@ class B200UNet:
 
     def _groupnorm(self, x1, C1, x2, C2, HW, g, b, eps, silu, out):
         NB, G = self._plan[0], self.spec.norm_num_groups
-        sums = self._buf("gn_sums", (NB, G, 2), torch.float32)
-        ops.gn_stats(x1, C1, x2, C2, NB, HW, G, sums)
-        ops.gn_apply(x1, C1, x2, C2, NB, HW, G, sums, g, b, eps, silu, out)
+        # two alternating statistics buffers: the first GroupNorm of a forward zeroes its own (one memset), every apply zeroes the
+        # buffer the next GroupNorm will accumulate into
+        k = self._gn_k
+        self._gn_k = k + 1
+        sums, nxt = self._buf(f"gn_sums{k & 1}", (NB, G, 2), torch.float32), self._buf(f"gn_sums{(k + 1) & 1}", (NB, G, 2), torch.float32)
+        ops.gn_stats(x1, C1, x2, C2, NB, HW, G, sums, zero_sums=(k == 0))
+        ops.gn_apply(x1, C1, x2, C2, NB, HW, G, sums, g, b, eps, silu, out, zero_next=nxt)
 
     def _resnet(self, r, x, skip, h, w, out_name, temb_all):
         """ResnetBlock2D on NHWC rows; ``skip`` = second source of the virtual channel concat (up path)."""
@@ -397,6 +402,7 @@ class B200UNet:
         NB, H, W = self._plan
         spec, P, buf = self.spec, self.params, self._buf
         kv = self._kv[key]
+        self._gn_k = 0
         down_res, mid_res = residuals
         emb, temb_all = self._time_embedding(key)
         # --- stem

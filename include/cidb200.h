@@ -27,6 +27,10 @@ typedef enum { CID_EPI_STORE = 0, CID_EPI_GEGLU = 1, CID_EPI_QKV = 2 } cid_epilo
 
 int cid_version(void);
 const char* cid_last_error(void);
+/* Scratch for the GEMM/conv tail balancing (split-K partial accumulators + arrival counters).  The library never allocates: the caller
+ * hands it a ZERO-FILLED device buffer (>= 4 KB; 24 MB covers every shape) that stays valid and untouched by others until it is replaced
+ * or cleared with (NULL, 0).  Without a workspace tiles are never split (same results, idle SMs in the last wave). */
+int cid_set_workspace(void* workspace, unsigned long long bytes);
 /* N-tile width the GEMM will use for (N, epilogue): GEGLU weights must be row-interleaved per tile of this width. */
 int cid_gemm_tile_n(int N, int epi);
 
@@ -60,11 +64,14 @@ int cid_attn_cross(const void* Q, long long q_pitch, const void* Kcat, const voi
 int cid_pack_cross_kv(const void* k_text, const void* v_text, const void* k_ip, const void* v_ip, void* k_cat,
                       void* vt_cat, int B, int C, int heads, int n_text, int n_ip, void* stream);
 
-/* GroupNorm over cat([x1 (C1), x2 (C2)]) NHWC: stats into sums[NB, groups, 2] (fp32; zeroed by the call), then
- * y = [silu](gn(x)).  Replaces ResnetBlock2D.norm1/norm2 + nonlinearity, Transformer2D.norm, conv_norm_out + conv_act. */
-int cid_gn_stats(const void* x1, int C1, const void* x2, int C2, int NB, int HW, int groups, float* sums, int dtype, void* stream);
+/* GroupNorm over cat([x1 (C1), x2 (C2)]) NHWC: stats accumulate into sums[NB, groups, 2] (fp32; zeroed by the call when zero_sums != 0,
+ * otherwise the caller guarantees zeros), then y = [silu](gn(x)); gn_apply also zeroes zero_next[NB, groups, 2] when non-NULL - two
+ * alternating buffers then need one memset per forward instead of one per GroupNorm.
+ * Replaces ResnetBlock2D.norm1/norm2 + nonlinearity, Transformer2D.norm, conv_norm_out + conv_act. */
+int cid_gn_stats(const void* x1, int C1, const void* x2, int C2, int NB, int HW, int groups, float* sums, int zero_sums, int dtype,
+                 void* stream);
 int cid_gn_apply(const void* x1, int C1, const void* x2, int C2, int NB, int HW, int groups, const float* sums,
-                 const void* gamma, const void* beta, float eps, int silu, void* y, int dtype, void* stream);
+                 const void* gamma, const void* beta, float eps, int silu, void* y, float* zero_next, int dtype, void* stream);
 int cid_layernorm(const void* x, const void* gamma, const void* beta, void* y, long long rows, int C, float eps, int dtype, void* stream);
 int cid_upsample2x(const void* x, void* y, int NB, int H, int W, int C, void* stream);
 int cid_phase_split(const void* x, void* y, int NB, int H, int W, int C, void* stream);

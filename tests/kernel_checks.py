@@ -199,6 +199,27 @@ def check_groupnorm(NB=2, HW=256, C1=320, C2=0, groups=32, silu=True, dtype=torc
     return _report(f"groupnorm NB{NB} HW{HW} C{C1}+{C2} silu{int(silu)} {str(dtype)[6:]}", out.reshape(-1, C), ref.reshape(-1, C), 5e-3)
 
 
+def check_groupnorm_chain(NB=3, HW=256, C=320, groups=32, n=5, dtype=torch.float16, eps=1e-5, seed=0):
+    """Alternating statistics buffers: only the first GroupNorm memsets, each apply zeroes the next one's buffer (unet._groupnorm)."""
+    ops = _ops()
+    bufs = [torch.full((NB, groups, 2), 123.0, dtype=torch.float32, device=DEV) for _ in range(2)]      # dirty on purpose
+    ga, be = _rand((C,), dtype, seed + 2) + 1, _rand((C,), dtype, seed + 3)
+    worst = None
+    for k in range(n):
+        x = _rand((NB, HW, C), dtype, seed + 10 + k) + 0.1 * k
+        out = torch.empty((NB, HW, C), dtype=dtype, device=DEV)
+        ops.gn_stats(x, C, None, 0, NB, HW, groups, bufs[k & 1], zero_sums=(k == 0))
+        ops.gn_apply(x, C, None, 0, NB, HW, groups, bufs[k & 1], ga, be, eps, True, out, zero_next=bufs[(k + 1) & 1])
+        torch.cuda.synchronize()
+        ref = F.silu(F.group_norm(x.float().permute(0, 2, 1), groups, ga.float(), be.float(), eps)).permute(0, 2, 1)
+        r = _report(f"groupnorm_chain step {k}", out.reshape(-1, C), ref.reshape(-1, C), 5e-3)
+        if worst is None or not r["ok"] or r["max_err"] > worst["max_err"]:
+            worst = r
+        if not r["ok"]:
+            break
+    return worst
+
+
 def check_layernorm(rows=1000, C=320, dtype=torch.float16, seed=0):
     ops = _ops()
     x = _rand((rows, C), dtype, seed) * 2 + 0.3
@@ -366,6 +387,16 @@ CHECKS = {
     "conv_out4": (check_conv, dict(NB=2, H=32, W=32, Cin=320, Cout=4)),
     "conv_1280": (check_conv, dict(NB=2, H=16, W=16, Cin=256, Cout=1280, rowbias=True, residual=True)),
     "gemm_n3840_qkv": (check_gemm_qkv, dict(B=1, ntok=256, C=1280, heads=20, dtype=B16)),
+    # tail balancing (split-K): shapes whose last wave is split into K-ranges (see gemm_tc2.cuh); each is run twice in a row by the
+    # battery/pytest process order, so the self-resetting arrival counters are exercised as well
+    "gemm_split_160t": (check_gemm, dict(M=4096, N=1280, K=5120, residual=True)),
+    "gemm_split_40t": (check_gemm, dict(M=1024, N=1280, K=2560, dtype=B16, rowbias=True)),
+    "gemm_split_ragged": (check_gemm, dict(M=2400, N=1200, K=2560, residual=True)),
+    "gemm_split_again": (check_gemm, dict(M=4096, N=1280, K=5120, residual=True, seed=7)),
+    "gemm_split_geglu": (check_gemm_geglu, dict(M=256, C=2560)),
+    "gemm_split_qkv": (check_gemm_qkv, dict(B=5, ntok=128, C=2560, heads=40)),
+    "conv_split_8x8": (check_conv, dict(NB=16, H=8, W=8, Cin=1280, Cout=1280, rowbias=True, residual=True)),
+    "conv_split_16x16": (check_conv, dict(NB=16, H=16, W=16, Cin=640, Cout=1280, dtype=B16)),
     "conv_s2": (check_conv, dict(NB=2, H=16, W=16, Cin=128, Cout=160, stride2=True)),
     "conv_s2_64": (check_conv, dict(NB=1, H=32, W=32, Cin=64, Cout=320, stride2=True, dtype=B16)),
     "attn_self_d64": (check_attn_self, dict(B=2, H=2, N=256, d=64)),
@@ -385,6 +416,7 @@ CHECKS = {
     "gn_concat": (check_groupnorm, dict(C1=640, C2=320, HW=1024)),
     "gn_2560": (check_groupnorm, dict(C1=1280, C2=1280, HW=64, NB=3, dtype=B16)),
     "gn_nosilu": (check_groupnorm, dict(C1=64, silu=False, eps=1e-6)),
+    "gn_chain": (check_groupnorm_chain, {}),
     "ln_320": (check_layernorm, dict(rows=1000, C=320)),
     "ln_1280": (check_layernorm, dict(rows=77, C=1280, dtype=B16)),
     "ln_64": (check_layernorm, dict(rows=33, C=64)),
