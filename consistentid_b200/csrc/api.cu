@@ -140,8 +140,12 @@ void* g_ws = nullptr;
 size_t g_ws_bytes = 0;
 constexpr size_t WS_COUNTER_BYTES = 4096;
 int env_int(const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; }
-int splitk_min_kb() { static const int v = env_int("CID_GEMM_SPLIT_MIN_KB", 16); return v < 1 ? 1 : v; }     // k-blocks per split unit
-int splitk_max() { static const int v = env_int("CID_GEMM_SPLITK", 8); return v; }                            // 0/1 disables
+// Measured (profiles/r01_splitk_sweep.txt): every extra K-range costs the finishing CTA ~3.5 us (its partial is read back from L2 with
+// little memory-level parallelism) and a tail tile running on an otherwise idle chip is ~1.6x faster than one in a full wave, so splitting
+// pays only for long K loops: >= 48 k-blocks (K >= 3072) per unit, at most 4 units.  GEMMs with K <= 5120 stay whole.
+int g_splitk_min_kb = -1, g_splitk_max = -1;            // -1: take the environment / default on first use; cid_set_splitk overrides
+int splitk_min_kb() { if (g_splitk_min_kb < 0) { g_splitk_min_kb = env_int("CID_GEMM_SPLIT_MIN_KB", 48); if (g_splitk_min_kb < 1) g_splitk_min_kb = 1; } return g_splitk_min_kb; }
+int splitk_max() { if (g_splitk_max < 0) { g_splitk_max = env_int("CID_GEMM_SPLITK", 4); if (g_splitk_max < 0) g_splitk_max = 0; } return g_splitk_max; }   // 0/1 disables
 
 template <int BN, int STAGES>
 int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
@@ -672,6 +676,13 @@ int cid_advance_step(int* step_dev, float* t_dev, const float* ts_table, int n, 
   if (!step_dev || !t_dev || !ts_table || n <= 0) return fail(CID_ERR_ARG, "cid_advance_step: bad arguments");
   advance_step_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(step_dev, t_dev, ts_table, n);
   CID_CHECK_LAUNCH("advance_step_kernel");
+  return 0;
+}
+
+int cid_set_splitk(int max_split, int min_kblocks) {
+  if (max_split > 64) return fail(CID_ERR_ARG, "cid_set_splitk: max_split=%d > 64", max_split);
+  g_splitk_max = max_split;                                   // negative: back to CID_GEMM_SPLITK / the default
+  g_splitk_min_kb = min_kblocks == 0 ? 1 : min_kblocks;       // negative: back to CID_GEMM_SPLIT_MIN_KB / the default
   return 0;
 }
 

@@ -35,6 +35,7 @@ _SIGS = {
     "cid_last_error": ([], C.c_char_p),
     "cid_gemm_tile_n": ([_i, _i], _i),
     "cid_set_workspace": ([_vp, C.c_ulonglong], _i),
+    "cid_set_splitk": ([_i, _i], _i),
     "cid_gemm": ([_vp, _ll, _vp, _ll, _i, _i, _vp, _vp, _ll, _i, _i, _vp, _vp, _ll, _vp, _i, _ll, _i, _vp, _i, _i, _i, _i, _f, _i, _vp], _i),
     "cid_conv3x3": ([_vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _ll, _vp, _ll, _f, _i, _vp], _i),
     "cid_attn_self": ([_vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp], _i),
@@ -82,6 +83,12 @@ def call(name, *args):
 
 def version() -> int:
     return _lib.cid_version()
+
+
+def set_splitk(max_split: int = -1, min_kblocks: int = -1) -> None:
+    """GEMM/conv tail-balancing policy (cid_set_splitk); defaults restore the library's measured settings."""
+    if _lib.cid_set_splitk(max_split, min_kblocks) != 0:
+        raise CidError(last_error())
 
 
 def gemm_tile_n(n: int, epi: int) -> int:

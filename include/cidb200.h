@@ -31,6 +31,9 @@ const char* cid_last_error(void);
  * hands it a ZERO-FILLED device buffer (>= 4 KB; 24 MB covers every shape) that stays valid and untouched by others until it is replaced
  * or cleared with (NULL, 0).  Without a workspace tiles are never split (same results, idle SMs in the last wave). */
 int cid_set_workspace(void* workspace, unsigned long long bytes);
+/* Tail-balancing policy: a tail tile is cut into at most max_split K-ranges of at least min_kblocks 64-wide k-blocks each (defaults 4 / 48,
+ * or CID_GEMM_SPLITK / CID_GEMM_SPLIT_MIN_KB); max_split <= 1 disables splitting, negative values restore the defaults. */
+int cid_set_splitk(int max_split, int min_kblocks);
 /* N-tile width the GEMM will use for (N, epilogue): GEGLU weights must be row-interleaved per tile of this width. */
 int cid_gemm_tile_n(int N, int epi);
 

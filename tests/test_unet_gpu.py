@@ -126,3 +126,26 @@ def test_denoise_loop_sdxl():
               pooled_text_only=pooled[1], pooled_facial=pooled[2], add_time_ids=tid)
     torch.cuda.synchronize()
     _cmp("loop sdxl euler", out, truth, eager)
+
+
+@pytest.mark.gpu
+def test_unet_forward_with_aggressive_tail_split():
+    """Whole UNet with every eligible GEMM/conv tail tile split along K (cid_set_splitk): same result up to fp32 summation order."""
+    from consistentid_b200 import lib
+    dtype = torch.float16
+    cfg = tiny_config("sd15")
+    ref = synth.build_ref_unet(cfg, rank=16)
+    B, h = 2, cfg.sample_size
+    null, aug, _ = synth.synth_prompts(cfg.cross_attention_dim)
+    x = synth.synth_latents(2 * B, h, h, seed=3).cuda().to(dtype)
+    ehs = torch.cat([null.expand(B, -1, -1), aug.expand(B, -1, -1)]).cuda().to(dtype)
+    eng = _engine_from_oracle(ref, dtype, 16)
+    base = eng(x, torch.tensor(601), ehs, cross_attention_kwargs={}).sample.float()
+    lib.set_splitk(8, 2)
+    try:
+        split = eng(x, torch.tensor(601), ehs, cross_attention_kwargs={}).sample.float()
+    finally:
+        lib.set_splitk(-1, -1)
+    torch.cuda.synchronize()
+    assert torch.isfinite(split).all()
+    assert (split - base).abs().max().item() <= 2e-2 * base.abs().max().item()
