@@ -26,6 +26,7 @@ class B200ControlNet(B200UNet):
         self.in_channels = spec.in_channels
         self.num_tokens, self.ip_scale = 0, 0.0          # default processors: every encoder row is a text row
         sd = state_dict
+        ops.ensure_workspace(self.device)
         P = _Params(spec, sd, None, dtype, self.device, rank=1, kinds=("down", "mid"), finalize=False)
         U = lambda n: sd[n].to(device=self.device, dtype=dtype)
         # conditioning embedding: channels zero-padded to multiples of 64 so the same implicit-GEMM conv kernel applies

@@ -156,6 +156,7 @@ class B200UNet:
         self.in_channels = spec.in_channels
         self.num_tokens, self.ip_scale = num_tokens, ip_scale
         self.params = _Params(spec, unet_state_dict, adapter_state_dict, dtype, self.device, rank, lora_scale)
+        ops.ensure_workspace(self.device)        # split-K scratch handed to the library now, never under CUDA-graph capture
         self._bufs = {}
         self._plan = None           # (NB, H, W)
         self._kv = {}               # prompt key -> per-layer (k_cat, vt_cat)
