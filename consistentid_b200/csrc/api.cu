@@ -706,6 +706,15 @@ int cid_layernorm_rows(const void* x, long long ldx, long long x_group_rows, lon
   return 0;
 }
 
+int cid_softmax_rows(void* x, long long ld, long long rows, int cols, int dtype, void* stream) {
+  if (!x || cols <= 0 || cols % 8 || ld % 8 || ld < cols || rows < 0 || rows > 0x7fffffffLL)
+    return fail(CID_ERR_ARG, "cid_softmax_rows: cols=%d and ld must be multiples of 8, ld >= cols", cols);
+  if (rows == 0) return 0;
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, static_cast<cudaStream_t>(stream)>>>((uint16_t*)x, ld, cols, dtype == CID_BF16);
+  CID_CHECK_LAUNCH("softmax_rows_kernel");
+  return 0;
+}
+
 int cid_perceiver_attn(const void* q, long long ldq, const void* kv, long long ldkv, void* out, long long ldo, int B, int L, int n_kv, int heads,
                        int dim_head, int dtype, void* stream) {
   if (!q || !kv || !out || dim_head != 64 || B <= 0 || L <= 0 || heads <= 0 || n_kv <= 0 || n_kv > 8192 || ldkv % 8)

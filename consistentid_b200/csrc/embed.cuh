@@ -103,4 +103,48 @@ perceiver_attn_kernel(const uint16_t* __restrict__ q, long long ldq, const uint1
   if (tid < 64) store16(out, (size_t)(b * L + l) * ldo + h * 64 + tid, part[0][tid] + part[1][tid], bf);
 }
 
+// In-place row softmax of a 16-bit matrix (fp32 math, one CTA per row, any cols % 8 == 0): the probabilities of the single-head,
+// d = 512 attention of the VAE mid block, whose scores are produced / consumed by two cid_gemm launches (diffusers Attention with
+// upcast_softmax).
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(uint16_t* __restrict__ x, long long ld, int cols, int bf) {
+  __shared__ float red[8];
+  uint16_t* row = x + (size_t)blockIdx.x * ld;
+  const int V = cols / 8, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float m = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += 256) {
+    float f[8]; unpack8(*reinterpret_cast<const uint4*>(row + v * 8), f, bf);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m = fmaxf(m, f[k]);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int v = threadIdx.x; v < V; v += 256) {
+    float f[8]; unpack8(*reinterpret_cast<const uint4*>(row + v * 8), f, bf);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += __expf(f[k] - m);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += red[w];
+  const float inv = 1.f / sum;
+  for (int v = threadIdx.x; v < V; v += 256) {
+    float f[8]; unpack8(*reinterpret_cast<const uint4*>(row + v * 8), f, bf);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = __expf(f[k] - m) * inv;
+    *reinterpret_cast<uint4*>(row + v * 8) = pack8(f, bf);
+  }
+}
+
 }  // namespace cid

@@ -58,6 +58,7 @@ _SIGS = {
     "cid_inpaint_blend": ([_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp], _i),
     "cid_layernorm_rows": ([_vp, _ll, _ll, _ll, _vp, _vp, _vp, _ll, _ll, _ll, _ll, _ll, _i, _f, _i, _vp], _i),
     "cid_perceiver_attn": ([_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp], _i),
+    "cid_softmax_rows": ([_vp, _ll, _ll, _i, _i, _vp], _i),
 }
 EXPORTS = tuple(_SIGS)
 for _name, (_args, _res) in _SIGS.items():

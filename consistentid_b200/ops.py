@@ -190,6 +190,12 @@ def layernorm_rows(x, gamma, beta, out, rows, C, eps=1e-5, rows_per_group=None, 
     return out
 
 
+def softmax_rows(x, rows, cols):
+    """In-place fp32-math softmax over the rows of the 16-bit matrix x[rows, cols] (row pitch x.stride(0))."""
+    call("cid_softmax_rows", _p(x), x.stride(0), rows, cols, _dt(x), _stream())
+    return x
+
+
 def perceiver_attn(q, kv, out, B, L, n_kv, heads, dim_head=64):
     """q [B*L, heads*64], kv [B*n_kv, 2*heads*64] (K | V), out [B*L, heads*64] (functions.py:446-453)."""
     call("cid_perceiver_attn", _p(q), q.stride(0), _p(kv), kv.stride(0), _p(out), out.stride(0), B, L, n_kv, heads, dim_head, _dt(q), _stream())

@@ -118,6 +118,11 @@ int cid_layernorm_rows(const void* x, long long ldx, long long x_group_rows, lon
 int cid_perceiver_attn(const void* q, long long ldq, const void* kv, long long ldkv, void* out, long long ldo, int B, int L, int n_kv, int heads,
                        int dim_head, int dtype, void* stream);
 
+/* ---- VAE decode: everything but this reuses cid_conv3x3 / cid_gemm / cid_gn_* / cid_upsample2x ---- */
+/* In-place softmax over each row of x[rows, cols] (pitch ld), fp32 math: probabilities of the single-head d=512 attention of the VAE mid
+ * block (diffusers Attention, upcast_softmax), between the Q.K^T and P.V cid_gemm launches. */
+int cid_softmax_rows(void* x, long long ld, long long rows, int cols, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -333,6 +333,17 @@ def check_perceiver_attn(B=2, L=4, n_kv=261, heads=3, dtype=torch.float16, seed=
     return _report(f"perceiver_attn B{B} L{L} n{n_kv} h{heads}", out, ref, 1e-2 if dtype == torch.float16 else 2.5e-2)
 
 
+def check_softmax_rows(rows=300, cols=4096, dtype=torch.float16, seed=0):
+    ops = _ops()
+    x = _rand((rows, cols + 64), dtype, seed, 3.0)                   # row pitch > cols
+    ref = torch.softmax(x[:, :cols].float(), dim=-1)
+    ops.softmax_rows(x, rows, cols)
+    torch.cuda.synchronize()
+    r = _report(f"softmax_rows {rows}x{cols}", x[:, :cols], ref, 4e-3)
+    r["ok"] = r["ok"] and abs(x[:, :cols].float().sum(-1) - 1).max().item() < 2e-2
+    return r
+
+
 def check_cfg_step(dtype=torch.float16, seed=0):
     ops = _ops()
     B, HW, CP = 3, 64, 64
@@ -397,6 +408,10 @@ CHECKS = {
     "gemm_split_qkv": (check_gemm_qkv, dict(B=5, ntok=128, C=2560, heads=40)),
     "conv_split_8x8": (check_conv, dict(NB=16, H=8, W=8, Cin=1280, Cout=1280, rowbias=True, residual=True)),
     "conv_split_16x16": (check_conv, dict(NB=16, H=16, W=16, Cin=640, Cout=1280, dtype=B16)),
+    "conv_w256": (check_conv, dict(NB=1, H=6, W=256, Cin=64, Cout=64, residual=True)),          # two 128-pixel strips per row (VAE resolutions)
+    "conv_w512_out3": (check_conv, dict(NB=1, H=4, W=512, Cin=128, Cout=3)),
+    "softmax_rows": (check_softmax_rows, dict(rows=300, cols=4096)),
+    "softmax_rows_64": (check_softmax_rows, dict(rows=64, cols=64, dtype=B16)),
     "conv_s2": (check_conv, dict(NB=2, H=16, W=16, Cin=128, Cout=160, stride2=True)),
     "conv_s2_64": (check_conv, dict(NB=1, H=32, W=32, Cin=64, Cout=320, stride2=True, dtype=B16)),
     "attn_self_d64": (check_attn_self, dict(B=2, H=2, N=256, d=64)),
