@@ -16,6 +16,8 @@ no CPU path.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -100,6 +102,34 @@ def _perceiver_stack(w, p, depth, heads, latents, x):
     return y.reshape(B, L, out_dim)
 
 
+class _GraphedStack:
+    """The perceiver stack is ~15 tiny launches per layer on 1-4 latent rows: launch-bound.  Per input shape it is captured once in a CUDA
+    graph (static input/output buffers) and replayed; CID_EMBED_GRAPH=0 keeps the eager launch sequence."""
+
+    def __init__(self, w, prefix, depth, heads):
+        self.w, self.prefix, self.depth, self.heads = w, prefix, depth, heads
+        self.cache = {}
+        self.enabled = os.environ.get("CID_EMBED_GRAPH", "1") != "0"
+
+    def __call__(self, latents, x):
+        if not self.enabled:
+            return _perceiver_stack(self.w, self.prefix, self.depth, self.heads, latents.clone(), x)
+        key = (tuple(latents.shape), tuple(x.shape), x.dtype)
+        ent = self.cache.get(key)
+        if ent is None:
+            lat_s, x_s = latents.clone().contiguous(), x.clone().contiguous()
+            _perceiver_stack(self.w, self.prefix, self.depth, self.heads, lat_s.clone(), x_s)      # warm-up outside the capture
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out_s = _perceiver_stack(self.w, self.prefix, self.depth, self.heads, lat_s, x_s)   # consumes lat_s in place
+            ent = self.cache[key] = (graph, lat_s, x_s, out_s)
+        graph, lat_s, x_s, out_s = ent
+        lat_s.copy_(latents); x_s.copy_(x)
+        graph.replay()
+        return out_s.clone()
+
+
 class ProjPlusModel:
     """functions.py:494-528 (``image_proj_model`` of the pipelines, pipline_StableDiffusion_ConsistentID.py:89-94)."""
 
@@ -111,9 +141,12 @@ class ProjPlusModel:
                   "norm.weight": (c,), "norm.bias": (c,)}
         shapes.update(_perceiver_shapes("perceiver_resampler.", c, self.depth, self.heads, clip_embeddings_dim, c))
         self.w = _Weights(shapes, dtype, device)
+        ops.ensure_workspace(self.w.device)
+        self._stack = _GraphedStack(self.w, "perceiver_resampler.", self.depth, self.heads)
 
     def load_state_dict(self, sd, strict=True):
         self.w.load_state_dict(sd, strict)
+        self._stack.cache.clear()            # captured graphs point at the previous weight tensors
         return self
 
     def state_dict(self):
@@ -129,7 +162,7 @@ class ProjPlusModel:
         h = ops.skinny_linear(idv, w["proj.0.weight"], w["proj.0.bias"], new(B, 2 * d), B, 2 * d, d)
         t = ops.skinny_linear(h, w["proj.2.weight"], w["proj.2.bias"], new(B, c * T), B, c * T, 2 * d, act_in="gelu")
         x = ops.layernorm_rows(t.view(B * T, c), w["norm.weight"], w["norm.bias"], new(B * T, c), B * T, c).view(B, T, c)
-        out = _perceiver_stack(w, "perceiver_resampler.", self.depth, self.heads, x.clone(), clip_embeds.contiguous())
+        out = self._stack(x, clip_embeds.contiguous())
         return torch.add(x, out, alpha=float(scale)) if shortcut else out
 
 
@@ -148,9 +181,12 @@ class FacialEncoder:
                            p + "fc2.weight": (D, D), p + "fc2.bias": (D,)})
         shapes.update({"fuse_module.layer_norm.weight": (D,), "fuse_module.layer_norm.bias": (D,)})
         self.w = _Weights(shapes, dtype, device)
+        ops.ensure_workspace(self.w.device)
+        self._stack = _GraphedStack(self.w, "visual_projection.", depth, heads)
 
     def load_state_dict(self, sd, strict=True):
         self.w.load_state_dict(sd, strict)
+        self._stack.cache.clear()            # captured graphs point at the previous weight tensors
         return self
 
     def state_dict(self):
@@ -161,7 +197,7 @@ class FacialEncoder:
         """AttentionMLP.forward: [n, tokens, embedding_dim] -> [n, 1, output_dim]."""
         _need_cuda16(x, "multi_image_embeds")
         lat = self.w["visual_projection.latents"].repeat(x.shape[0], 1, 1)
-        return _perceiver_stack(self.w, "visual_projection.", self.depth, self.heads, lat, x.contiguous())
+        return self._stack(lat, x.contiguous())
 
     def _mlp(self, p, x, residual):
         w, m, D = self.w, x.shape[0], self.embed_dim
