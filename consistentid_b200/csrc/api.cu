@@ -650,9 +650,18 @@ int cid_skinny_linear(const void* x, long long ldx, const void* W, const void* b
   if (!x || !W || !y || K % 8 || K > 8192 || M <= 0) return fail(CID_ERR_ARG, "cid_skinny_linear: K=%d must be a multiple of 8 and <= 8192", K);
   const int slab = K <= 4096 ? 16 : 8;           // rows of x staged per pass: slab * K * 2 bytes of shared memory (<= 128 KB)
   static bool configured = false;
-  if (!configured) { int rc = set_smem(skinny_linear_kernel, 16 * 4096 * 2, "skinny_linear_kernel"); if (rc) return rc; configured = true; }
-  skinny_linear_kernel<<<(N + 7) / 8, 256, (size_t)slab * K * 2, static_cast<cudaStream_t>(stream)>>>(
-      (const uint16_t*)x, ldx, (const uint16_t*)W, (const uint16_t*)bias, (uint16_t*)y, ldy, M, N, K, silu_in, accumulate, dtype == CID_BF16, slab);
+  if (!configured) {
+    int rc = set_smem(skinny_linear_kernel, 16 * 4096 * 2, "skinny_linear_kernel"); if (rc) return rc;
+    rc = set_smem(skinny_linear2_kernel, 16 * 4096 * 2, "skinny_linear2_kernel"); if (rc) return rc;
+    configured = true;
+  }
+  static const int version = env_int("CID_SKINNY_VERSION", 1);       // 2 = software-pipelined weight stream (elementwise.cuh)
+  if (version == 2)
+    skinny_linear2_kernel<<<(N + 7) / 8, 256, (size_t)slab * K * 2, static_cast<cudaStream_t>(stream)>>>(
+        (const uint16_t*)x, ldx, (const uint16_t*)W, (const uint16_t*)bias, (uint16_t*)y, ldy, M, N, K, silu_in, accumulate, dtype == CID_BF16, slab);
+  else
+    skinny_linear_kernel<<<(N + 7) / 8, 256, (size_t)slab * K * 2, static_cast<cudaStream_t>(stream)>>>(
+        (const uint16_t*)x, ldx, (const uint16_t*)W, (const uint16_t*)bias, (uint16_t*)y, ldy, M, N, K, silu_in, accumulate, dtype == CID_BF16, slab);
   CID_CHECK_LAUNCH("skinny_linear_kernel");
   return 0;
 }

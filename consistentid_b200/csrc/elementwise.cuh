@@ -346,6 +346,86 @@ skinny_linear_kernel(const uint16_t* __restrict__ x, long long ldx, const uint16
   }
 }
 
+// v2 of skinny_linear_kernel (same arguments, same math): the weight stream is software-pipelined - four 16-byte loads per lane are in
+// flight before the FMAs of the first one start - and x is staged with 16-byte copies instead of per-element index arithmetic.  The
+// embedding producers stream 250-600 MB of weights through this kernel on <= 10 rows, where v1 is bound by the load -> FMA dependency chain.
+__global__ void __launch_bounds__(256)
+skinny_linear2_kernel(const uint16_t* __restrict__ x, long long ldx, const uint16_t* __restrict__ w, const uint16_t* __restrict__ bias,
+                      uint16_t* __restrict__ y, long long ldy, int M, int N, int K, int act_in, int accumulate, int bf, int slab) {
+  extern __shared__ uint16_t xs[];               // [slab][K], slab <= 16
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int V = K / 8;
+  const bool x_vec = (ldx % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  for (int m0 = 0; m0 < M; m0 += slab) {
+    const int mrows = min(slab, M - m0);
+    __syncthreads();
+    for (int r = 0; r < mrows; ++r) {
+      const uint16_t* xr = x + (size_t)(m0 + r) * ldx;
+      for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        float f[8];
+        if (x_vec) unpack8(*reinterpret_cast<const uint4*>(xr + v * 8), f, bf);
+        else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = load16(xr, v * 8 + e, bf);
+        }
+        if (act_in == 1) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
+        } else if (act_in == 2) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = 0.5f * f[e] * (1.f + erff(f[e] * 0.70710678118654752f));
+        }
+        *reinterpret_cast<uint4*>(xs + (size_t)r * K + v * 8) = pack8(f, bf);
+      }
+    }
+    __syncthreads();
+    if (col < N) {
+      float acc[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) acc[r] = 0.f;
+      const uint16_t* wr = w + (size_t)col * K;
+      for (int k0 = lane * 8; k0 < K; k0 += 1024) {
+        uint4 wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u * 256;
+          wv[u] = (k < K) ? *reinterpret_cast<const uint4*>(wr + k) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u * 256;
+          if (k < K) {
+            float wf[8]; unpack8(wv[u], wf, bf);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+              if (r < mrows) {
+                float xf[8]; unpack8(*reinterpret_cast<const uint4*>(xs + (size_t)r * K + k), xf, bf);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[r] += wf[e] * xf[e];
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+      }
+      if (lane == 0) {
+        const float bv = bias ? load16(bias, col, bf) : 0.f;
+        for (int r = 0; r < mrows; ++r) {
+          float v = acc[r] + bv;
+          const size_t o = (size_t)(m0 + r) * ldy + col;
+          if (accumulate) v += load16(y, o, bf);
+          store16(y, o, v, bf);
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ cross-attn K/V packing
 // K_cat[b, 96, C]: rows [0,77) = text keys, [80,84) = id keys, rest 0.   Vt_cat[b*H + h, d, 96]: same columns, transposed.
 __global__ void __launch_bounds__(256)

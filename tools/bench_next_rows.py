@@ -29,8 +29,9 @@ def init(shapes, seed):
             for n, s in shapes.items()}
 
 
-for name, cfg, B, h, dt in (("vae_decode sd15 512x512 batch 8 fp16", sd15_vae_config(), 8, 64, torch.float16),
-                            ("vae_decode sdxl 1024x1024 batch 4 bf16", sdxl_vae_config(), 4, 128, torch.bfloat16)):
+VAE_CASES = () if os.environ.get("SKIP_VAE") else (("vae_decode sd15 512x512 batch 8 fp16", sd15_vae_config(), 8, 64, torch.float16),
+                            ("vae_decode sdxl 1024x1024 batch 4 bf16", sdxl_vae_config(), 4, 128, torch.bfloat16))
+for name, cfg, B, h, dt in VAE_CASES:
     try:
         ref16 = build_ref_vae(cfg, dtype=dt).to(dev)
         eng = B200VAEDecoder(ref16.state_dict(), scaling_factor=cfg.scaling_factor, dtype=dt)
