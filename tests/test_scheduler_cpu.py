@@ -42,3 +42,19 @@ def test_add_noise_euler():
     x0, n = torch.randn(2, 4, 4, 4), torch.randn(2, 4, 4, 4)
     t = ref.timesteps[[3, 17]]
     assert torch.allclose(ref.add_noise(x0, n, t), ours.add_noise(x0, n, t), rtol=1e-5, atol=1e-5)
+
+
+def test_published_schedule_constants():
+    """Known-answer anchors of the Stable Diffusion noise schedule (scaled_linear betas 0.00085..0.012, 1000 steps) that every SD
+    implementation publishes: alpha_bar_0 = 0.99915, alpha_bar_999 = 0.00466, sigma_max = 14.6146, sigma_min = 0.0292."""
+    from oracle.schedulers_ref import sd_alphas_cumprod
+    for acp in (sched.alphas_cumprod(), sd_alphas_cumprod().double().numpy()):
+        assert abs(acp[0] - 0.99915) < 1e-5 and abs(acp[999] - 0.00466) < 1e-5
+        assert abs(((1 - acp[999]) / acp[999]) ** 0.5 - 14.6146) < 1e-3
+        assert abs(((1 - acp[0]) / acp[0]) ** 0.5 - 0.0292) < 1e-4
+    s = sched.B200Scheduler("euler")
+    s.set_timesteps(1000)                       # leading spacing + steps_offset 1: t = 1000 .. 1, the first one clamps to the table end
+    assert abs(s.sigmas[0] - 14.6146) < 1e-3 and s.sigmas[-1] == 0.0 and abs(s.init_noise_sigma - (14.6146 ** 2 + 1) ** 0.5) < 1e-3
+    d = sched.B200Scheduler("ddim")
+    d.set_timesteps(50)
+    assert list(d.timesteps[:3].tolist()) == [981, 961, 941] and int(d.timesteps[-1]) == 1     # leading spacing, steps_offset 1
