@@ -261,3 +261,11 @@ def install(monkeypatch):
     for n in _NAMES:
         monkeypatch.setattr(ops, n, globals()[n])
     monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+
+
+def install_permanent():
+    """Same as ``install`` for a throw-away process (spawned distributed workers): no restore."""
+    from consistentid_b200 import ops
+    for n in _NAMES:
+        setattr(ops, n, globals()[n])
+    torch.Tensor.is_cuda = property(lambda self: True)
