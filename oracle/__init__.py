@@ -11,7 +11,7 @@ What is restated here
 ---------------------
 * ``processors_ref``  - the reference's own code for the path:
   ``attention.py:90-174`` (Consistent_AttProcessor) and ``attention.py:177-294``
-  (Consistent_IPAttProcessor).  PINNED: ``tests/test_oracle_vs_reference.py``
+  (Consistent_IPAttProcessor).  PINNED: ``tests/test_oracle_cpu.py``
   imports the reference ``attention.py`` verbatim (through the 2-symbol
   ``oracle/diffusers_shim``) and compares, and ``tests/golden/*.pt`` hold
   outputs generated from that verbatim import (``tests/golden/make_golden.py``).
@@ -24,4 +24,12 @@ What is restated here
   ``pipline_StableDiffusion_ConsistentID.py:536-579``,
   ``pipline_StableDiffusionXL_ConsistentID.py:611-667``).
 * ``loop_ref`` - the denoising-loop bodies of the reference pipelines.
+* ``controlnet_ref`` - diffusers ``ControlNetModel`` with default processors (config 5; unpinned like ``unet_ref``).
+* ``embed_ref`` - the embedding producers ``ProjPlusModel`` / ``AttentionMLP`` / ``FuseModule`` / ``FacialEncoder``
+  (``functions.py:389-592``, ``attention.py:10-88``).  PINNED on golden vectors generated from the reference's own classes
+  (``tests/golden/make_embed_golden.py``).
+* ``clip_ref`` - CLIP ViT image encoder up to ``hidden_states[-2]``.  PINNED on the ``transformers`` implementation installed in this
+  image (``tests/test_clip_cpu.py``).
+* ``vae_ref`` - diffusers ``AutoencoderKL`` decode (unpinned; anchored on the decoder's published 49,490,179 parameters).
+* ``synth`` - seeded synthetic weights / prompts / latents.
 """
