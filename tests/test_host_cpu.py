@@ -83,3 +83,17 @@ def test_walk_channel_bookkeeping():
     ups = {s.name: [[r.cin for r, _ in layers] for kind, _, layers, _ in walk(s) if kind == "up"] for s in (sd15_spec(), sdxl_spec())}
     assert ups["sd15"] == [[2560, 2560, 2560], [2560, 2560, 1920], [1920, 1280, 960], [960, 640, 640]]
     assert ups["sdxl"] == [[2560, 2560, 1920], [1920, 1280, 960], [960, 640, 640]]
+
+
+def test_product_never_touches_the_oracle_or_a_compiler_stack():
+    """The oracle is test infrastructure; the product has no CPU fallback, no Triton / torch.compile path."""
+    import glob
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bad = re.compile(r"^\s*(from|import)\s+(oracle|triton|tilelang)\b|torch\.compile\(", re.M)
+    for path in glob.glob(os.path.join(root, "consistentid_b200", "**", "*.py"), recursive=True):
+        src = open(path).read()
+        assert not bad.search(src), path
+    entry = open(os.path.join(root, "__graft_entry__.py")).read()
+    assert "def build" in entry and "def smoke" in entry and "compute_100a" in entry
