@@ -58,6 +58,7 @@ class B200ControlNet(B200UNet):
         self._slots, self._ident, self._auto_next = {}, {}, 0
         self._procs = {}
         self._cond = None
+        self.plan_epoch = 0
 
     # ------------------------------------------------------------------ control image (once per generation)
     def set_control_image(self, control_image):
@@ -88,6 +89,7 @@ class B200ControlNet(B200UNet):
     def plan(self, NB, H, W):
         if self._plan != (NB, H, W):
             self._plan = (NB, H, W)
+            self.plan_epoch = getattr(self, "plan_epoch", 0) + 1
             self._kv.clear(); self._aug.clear(); self._slots.clear(); self._ident.clear()
             keep = {k: v for k, v in self._bufs.items() if k[0] == "t_dev"}
             self._bufs = keep

@@ -11,16 +11,11 @@
 #include <cudaTypedefs.h>
 
 #include "../../include/cidb200.h"
-#include "attn_tc.cuh"
-#include "attn_tc2.cuh"
+#include "attn_cross.cuh"
 #include "attn_tc3.cuh"
 #include "elementwise.cuh"
 #include "embed.cuh"
-#include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
-#include "gemm_tc3.cuh"
-#include "gemm_tc4.cuh"
-#include "gemm_tc5.cuh"
 
 using namespace cid;
 
@@ -38,11 +33,7 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 // Programmatic dependent launch (see common.cuh): kernels that call griddep_wait() before touching global memory are launched with
-// cudaLaunchAttributeProgrammaticStreamSerialization so their prologue overlaps the predecessor's tail.  CID_PDL=0 disables it.
-bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("CID_PDL"); return !(e && e[0] == '0'); }();
-  return on;
-}
+// cudaLaunchAttributeProgrammaticStreamSerialization so their prologue overlaps the predecessor's tail.
 template <typename... KArgs, typename... Args>
 void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -50,7 +41,7 @@ void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cu
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);   // error picked up by CID_CHECK_LAUNCH
 }
 
@@ -86,10 +77,17 @@ int map_2d(CUtensorMap* m, const void* base, long long inner, long long rows, lo
   return make_map(m, base, 2, dims, str, box);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: remember it per (kernel, device) so that one
+// process may drive several GPUs through this library.
+constexpr int MAX_DEVICES = 64;
+int current_device() { int d = 0; return cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < MAX_DEVICES ? d : 0; }
 template <typename K>
-int set_smem(K kernel, int bytes, const char* name) {
+int set_smem(K kernel, int bytes, const char* name, bool (&done)[MAX_DEVICES]) {
+  const int dev = current_device();
+  if (done[dev]) return 0;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return fail(CID_ERR_CUDA, "cudaFuncSetAttribute(%s, %d B): %s", name, bytes, cudaGetErrorString(e));
+  done[dev] = true;
   return 0;
 }
 
@@ -99,63 +97,28 @@ int grid_for(long long work_items, int block) {
   return int(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-template <int BN, int STAGES>
-int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
-  using SM = GemmSmem<BN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    int rc = set_smem(gemm_tc_kernel<BN, STAGES>, SM::TOTAL, "gemm_tc_kernel");
-    if (rc) return rc;
-    configured = true;
-  }
-  dim3 grid((g.N + BN - 1) / BN, m_tiles);
-  gemm_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, SM::TOTAL, st>>>(a1, a2, b, g);
-  CID_CHECK_LAUNCH("gemm_tc_kernel");
-  return 0;
-}
-int g_num_sms = 0;
+int g_num_sms[MAX_DEVICES] = {};
 int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) g_num_sms = n;
-    else g_num_sms = 148;
+  const int dev = current_device();
+  if (g_num_sms[dev] == 0) {
+    int n = 0;
+    g_num_sms[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
   }
-  return g_num_sms;
-}
-// 1 = one-tile-per-CTA kernel (gemm_tc.cuh), 2 = persistent 1-CTA kernel (gemm_tc2.cuh, DEFAULT),
-// 3 = persistent 2-CTA pairs (gemm_tc3.cuh; parity-green, measured no faster than 2 on B200 - see DESIGN.md),
-// 4 = version 2 with two k-blocks per TMA instruction for the 160/64-wide tiles (gemm_tc4.cuh; parity-green, ~neutral),
-// 5 = version 2 with a row-coalesced smem-staged epilogue (gemm_tc5.cuh; parity-green, measured SLOWER except for the QKV epilogue)
-int g_gemm_version = 0;
-int gemm_version() {
-  if (g_gemm_version == 0) {
-    const char* e = getenv("CID_GEMM_VERSION");
-    g_gemm_version = (e && e[0] >= '1' && e[0] <= '5') ? (e[0] - '0') : 2;
-  }
-  return g_gemm_version;
+  return g_num_sms[dev];
 }
 
-// Split-K workspace (caller-provided through cid_set_workspace; the library never allocates): [4 KB counters | fp32 partials]
-void* g_ws = nullptr;
-size_t g_ws_bytes = 0;
+// Split-K tail-balancing policy.  Measured (profiles/r01_splitk_sweep.txt): every extra K-range costs the finishing CTA ~3.5 us and a tail
+// tile running on an otherwise idle chip is ~1.6x faster than one in a full wave, so splitting pays only for long K loops: >= 48 k-blocks
+// (K >= 3072) per unit, at most 4 units.  cid_set_splitk overrides (tests force it on to exercise the path).
 constexpr size_t WS_COUNTER_BYTES = 4096;
-int env_int(const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; }
-// Measured (profiles/r01_splitk_sweep.txt): every extra K-range costs the finishing CTA ~3.5 us (its partial is read back from L2 with
-// little memory-level parallelism) and a tail tile running on an otherwise idle chip is ~1.6x faster than one in a full wave, so splitting
-// pays only for long K loops: >= 48 k-blocks (K >= 3072) per unit, at most 4 units.  GEMMs with K <= 5120 stay whole.
-int g_splitk_min_kb = -1, g_splitk_max = -1;            // -1: take the environment / default on first use; cid_set_splitk overrides
-int splitk_min_kb() { if (g_splitk_min_kb < 0) { g_splitk_min_kb = env_int("CID_GEMM_SPLIT_MIN_KB", 48); if (g_splitk_min_kb < 1) g_splitk_min_kb = 1; } return g_splitk_min_kb; }
-int splitk_max() { if (g_splitk_max < 0) { g_splitk_max = env_int("CID_GEMM_SPLITK", 4); if (g_splitk_max < 0) g_splitk_max = 0; } return g_splitk_max; }   // 0/1 disables
+int g_splitk_min_kb = 48, g_splitk_max = 4;
 
 template <int BN, int STAGES>
-int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
+int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, void* ws, size_t ws_bytes,
+                 cudaStream_t st) {
   using SM = Gemm2Smem<BN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    int rc = set_smem(gemm_tc2_kernel<BN, STAGES>, SM::TOTAL, "gemm_tc2_kernel");
-    if (rc) return rc;
-    configured = true;
-  }
+  static bool configured[MAX_DEVICES] = {};
+  if (int rc = set_smem(gemm_tc2_kernel<BN, STAGES>, SM::TOTAL, "gemm_tc2_kernel", configured)) return rc;
   const int n_tiles = (g.N + BN - 1) / BN;
   const int total = n_tiles * m_tiles;
   const int G = num_sms();
@@ -164,17 +127,17 @@ int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap
   if (total >= G) { grid = G; sched.full_iters = total / G; sched.tail_tiles = total % G; }
   else { grid = total; sched.full_iters = 0; sched.tail_tiles = total; }
   sched.ksplit = 1;
-  // tail balancing: cut each tail tile into K-ranges so that (almost) every SM gets a share (see gemm_tc2.cuh)
-  if (sched.tail_tiles > 0 && g_ws != nullptr && splitk_max() > 1) {
+  // tail balancing: cut each tail tile into K-ranges so that (almost) every SM gets a share (see gemm_tc2.cuh); needs the caller's workspace
+  if (sched.tail_tiles > 0 && ws != nullptr && ws_bytes > WS_COUNTER_BYTES && g_splitk_max > 1) {
     const int num_kb = g.taps * (g.kblocks_a1 + g.kblocks_a2);
     int sp = G / sched.tail_tiles;
-    if (sp > num_kb / splitk_min_kb()) sp = num_kb / splitk_min_kb();
-    if (sp > splitk_max()) sp = splitk_max();
+    if (sp > num_kb / g_splitk_min_kb) sp = num_kb / g_splitk_min_kb;
+    if (sp > g_splitk_max) sp = g_splitk_max;
     const size_t need = WS_COUNTER_BYTES + (size_t)sched.tail_tiles * sp * GEMM_BM * BN * sizeof(float);
-    if (sp >= 2 && sched.tail_tiles * sizeof(int) <= WS_COUNTER_BYTES && need <= g_ws_bytes) {
+    if (sp >= 2 && sched.tail_tiles * sizeof(int) <= WS_COUNTER_BYTES && need <= ws_bytes) {
       sched.ksplit = sp;
-      sched.counters = reinterpret_cast<int*>(g_ws);
-      sched.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(g_ws) + WS_COUNTER_BYTES);
+      sched.counters = reinterpret_cast<int*>(ws);
+      sched.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + WS_COUNTER_BYTES);
       if (sched.tail_tiles * sp > grid) grid = sched.tail_tiles * sp;
     }
   }
@@ -183,110 +146,20 @@ int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap
   return 0;
 }
 
-template <int BN, int STAGES>
-int launch_gemm3(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
-  using SM = Gemm3Smem<BN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    int rc = set_smem(gemm_tc3_kernel<BN, STAGES>, SM::TOTAL, "gemm_tc3_kernel");
-    if (rc) return rc;
-    configured = true;
-  }
-  const int n_tiles = (g.N + BN - 1) / BN;
-  const int total = n_tiles * ((m_tiles + 1) / 2);            // 256-row pair tiles
-  const int max_pairs = num_sms() / 2;
-  const int pairs = total < max_pairs ? total : max_pairs;
-  gemm_tc3_kernel<BN, STAGES><<<2 * pairs, GEMM2_THREADS, SM::TOTAL, st>>>(a1, a2, b, g, n_tiles, total);
-  CID_CHECK_LAUNCH("gemm_tc3_kernel");
-  return 0;
-}
-// rows of B staged per CTA (= TMA box height of the weight map)
-int b_box_rows(int bn) { return (gemm_version() == 3 && bn >= 32) ? bn / 2 : bn; }
-
-template <int BN, int STAGES>
-int launch_gemm5(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
-  using SM = Gemm5Smem<BN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    int rc = set_smem(gemm_tc5_kernel<BN, STAGES>, SM::TOTAL, "gemm_tc5_kernel");
-    if (rc) return rc;
-    configured = true;
-  }
-  const int n_tiles = (g.N + BN - 1) / BN;
-  const int total = n_tiles * m_tiles;
-  const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc5_kernel<BN, STAGES><<<grid, GEMM2_THREADS, SM::TOTAL, st>>>(a1, a2, b, g, n_tiles, total);
-  CID_CHECK_LAUNCH("gemm_tc5_kernel");
-  return 0;
-}
-// the coalesced epilogue moves whole 16-byte segments: needs 8-element granularity everywhere
-bool v5_ok(int bn, const GemmArgs& g) {
-  const int n_out = g.epi == EPI_GEGLU ? g.N / 2 : g.N;
-  return gemm_version() == 5 && bn >= 64 && n_out % 8 == 0 && g.ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 &&
-         (!g.residual || (g.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(g.residual) & 15) == 0)) &&
-         (g.epi != EPI_QKV || g.n_split % 8 == 0);
-}
-
-template <int BN, int STAGES, int KPI>
-int launch_gemm4(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
-  using SM = Gemm4Smem<BN, STAGES, KPI>;
-  static bool configured = false;
-  if (!configured) {
-    int rc = set_smem(gemm_tc4_kernel<BN, STAGES, KPI>, SM::TOTAL, "gemm_tc4_kernel");
-    if (rc) return rc;
-    configured = true;
-  }
-  const int n_tiles = (g.N + BN - 1) / BN;
-  const int total = n_tiles * m_tiles;
-  const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc4_kernel<BN, STAGES, KPI><<<grid, GEMM2_THREADS, SM::TOTAL, st>>>(a1, a2, b, g, n_tiles, total);
-  CID_CHECK_LAUNCH("gemm_tc4_kernel");
-  return 0;
-}
-// [rows, K] operand viewed as {64, rows, K/64}: box {64, box_rows, 2} = two k-blocks per TMA instruction
-int map_3d_k(CUtensorMap* m, const void* base, long long K, long long rows, long long pitch_elems, int box_rows) {
-  cuuint64_t dims[3] = {64, cuuint64_t(rows), cuuint64_t(K / 64)};
-  cuuint64_t str[2] = {cuuint64_t(pitch_elems) * 2, 128};
-  cuuint32_t box[3] = {64, cuuint32_t(box_rows), 2};
-  return make_map(m, base, 3, dims, str, box);
-}
-bool use_v4(int bn) { return gemm_version() == 4 && (bn == 160 || bn == 64); }
-int dispatch_gemm4(int bn, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
-  if (bn == 160) return launch_gemm4<160, 3, 2>(a1, a2, b, g, m_tiles, st);
-  return launch_gemm4<64, 4, 2>(a1, a2, b, g, m_tiles, st);
-}
-
-int dispatch_gemm(int bn, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, cudaStream_t st) {
-  if (gemm_version() == 3 && bn >= 32) {
-    switch (bn) {
-      case 256: return launch_gemm3<256, 6>(a1, a2, b, g, m_tiles, st);
-      case 160: return launch_gemm3<160, 7>(a1, a2, b, g, m_tiles, st);
-      case 64: return launch_gemm3<64, 8>(a1, a2, b, g, m_tiles, st);
-    }
-    return fail(CID_ERR_UNSUPPORTED, "no 2-CTA GEMM instantiation for tile N %d", bn);
-  }
-  if (v5_ok(bn, g)) {
-    switch (bn) {
-      case 256: return launch_gemm5<256, 3>(a1, a2, b, g, m_tiles, st);
-      case 160: return launch_gemm5<160, 4>(a1, a2, b, g, m_tiles, st);
-      case 64: return launch_gemm5<64, 8>(a1, a2, b, g, m_tiles, st);
-    }
-  }
-  if (gemm_version() >= 2) {      // (versions 4 / 5 fall through to the v2 kernel for tiles they do not cover)
-    switch (bn) {
-      case 256: return launch_gemm2<256, 4>(a1, a2, b, g, m_tiles, st);
-      case 160: return launch_gemm2<160, 5>(a1, a2, b, g, m_tiles, st);
-      case 64: return launch_gemm2<64, 8>(a1, a2, b, g, m_tiles, st);
-      case 16: return launch_gemm2<16, 8>(a1, a2, b, g, m_tiles, st);
-    }
-    return fail(CID_ERR_UNSUPPORTED, "no GEMM instantiation for tile N %d", bn);
-  }
+int dispatch_gemm(int bn, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, void* ws,
+                  size_t ws_bytes, cudaStream_t st) {
   switch (bn) {
-    case 160: return launch_gemm<160, 3>(a1, a2, b, g, m_tiles, st);
-    case 64: return launch_gemm<64, 4>(a1, a2, b, g, m_tiles, st);
-    case 16: return launch_gemm<16, 4>(a1, a2, b, g, m_tiles, st);
+    case 256: return launch_gemm2<256, 4>(a1, a2, b, g, m_tiles, ws, ws_bytes, st);
+    case 160: return launch_gemm2<160, 5>(a1, a2, b, g, m_tiles, ws, ws_bytes, st);
+    case 64: return launch_gemm2<64, 8>(a1, a2, b, g, m_tiles, ws, ws_bytes, st);
+    case 16: return launch_gemm2<16, 8>(a1, a2, b, g, m_tiles, ws, ws_bytes, st);
   }
   return fail(CID_ERR_UNSUPPORTED, "no GEMM instantiation for tile N %d", bn);
+}
+int check_ws(const void* ws, size_t ws_bytes, const char* who) {
+  if (ws != nullptr && (reinterpret_cast<uintptr_t>(ws) % 256 || ws_bytes < WS_COUNTER_BYTES))
+    return fail(CID_ERR_ARG, "%s: workspace must be 256-byte aligned and >= %zu bytes (or NULL)", who, WS_COUNTER_BYTES);
+  return 0;
 }
 
 int d_pad_for(int d) {
@@ -301,35 +174,10 @@ int d_pad_for(int d) {
 }
 
 template <int D_PAD>
-int launch_attn_self(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
-  using C = AttnCfg<D_PAD>;
-  static bool configured = false;
-  if (!configured) { int rc = set_smem(attn_self_kernel<D_PAD>, C::TOTAL, "attn_self_kernel"); if (rc) return rc; configured = true; }
-  dim3 grid((a.Nq + 127) / 128, a.H, a.B);
-  attn_self_kernel<D_PAD><<<grid, ATTN_THREADS, C::TOTAL, st>>>(q, k, v, a);
-  CID_CHECK_LAUNCH("attn_self_kernel");
-  return 0;
-}
-int g_attn_version = 0;
-int attn_version() {
-  if (g_attn_version == 0) { const char* e = getenv("CID_ATTN_VERSION"); g_attn_version = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 3; }
-  return g_attn_version;
-}
-template <int D_PAD>
-int launch_attn_self2(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
-  using C = Attn2Cfg<D_PAD>;
-  static bool configured = false;
-  if (!configured) { int rc = set_smem(attn_self2_kernel<D_PAD>, C::TOTAL, "attn_self2_kernel"); if (rc) return rc; configured = true; }
-  dim3 grid((a.Nq + 127) / 128, a.H, a.B);
-  attn_self2_kernel<D_PAD><<<grid, ATTN_THREADS, C::TOTAL, st>>>(q, k, v, a);
-  CID_CHECK_LAUNCH("attn_self2_kernel");
-  return 0;
-}
-template <int D_PAD>
 int launch_attn_self3(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
   using C = Attn2Cfg<D_PAD>;
-  static bool configured = false;
-  if (!configured) { int rc = set_smem(attn_self3_kernel<D_PAD>, C::TOTAL, "attn_self3_kernel"); if (rc) return rc; configured = true; }
+  static bool configured[MAX_DEVICES] = {};
+  if (int rc = set_smem(attn_self3_kernel<D_PAD>, C::TOTAL, "attn_self3_kernel", configured)) return rc;
   dim3 grid((a.Nq + 127) / 128, a.H, a.B);
   launch_pdl(attn_self3_kernel<D_PAD>, dim3(grid), dim3(ATTN_THREADS), C::TOTAL, st, q, k, v, a);
   CID_CHECK_LAUNCH("attn_self3_kernel");
@@ -338,8 +186,8 @@ int launch_attn_self3(const CUtensorMap& q, const CUtensorMap& k, const CUtensor
 template <int D_PAD>
 int launch_attn_cross(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
   using C = CrossCfg<D_PAD>;
-  static bool configured = false;
-  if (!configured) { int rc = set_smem(attn_cross_kernel<D_PAD>, C::TOTAL, "attn_cross_kernel"); if (rc) return rc; configured = true; }
+  static bool configured[MAX_DEVICES] = {};
+  if (int rc = set_smem(attn_cross_kernel<D_PAD>, C::TOTAL, "attn_cross_kernel", configured)) return rc;
   dim3 grid((a.Nq + 127) / 128, a.H, a.B);
   launch_pdl(attn_cross_kernel<D_PAD>, dim3(grid), dim3(128), C::TOTAL, st, q, k, v, a);
   CID_CHECK_LAUNCH("attn_cross_kernel");
@@ -369,9 +217,7 @@ const char* cid_last_error(void) { return g_err; }
 
 int cid_gemm_tile_n(int N, int epi) {
   // 256-wide tiles cut the L2->SMEM bytes per FLOP (the limiter of the 128x160 tile) wherever the width allows
-  static int allow256 = -1;
-  if (allow256 < 0) { const char* e = getenv("CID_GEMM_NO256"); allow256 = (e && e[0] == '1') ? 0 : 1; }
-  if (allow256 && gemm_version() >= 2 && N % 256 == 0 && N >= 1024) return 256;
+  if (N % 256 == 0 && N >= 1024) return 256;
   if (epi == CID_EPI_GEGLU) {
     if (N % 160 == 0) return 160;
     if (N % 64 == 0) return 64;
@@ -386,8 +232,9 @@ int cid_gemm_tile_n(int N, int epi) {
 int cid_gemm(const void* A, long long lda, const void* A2, long long lda2, int K1, int K2, const void* B, void* C,
              long long ldc, int M, int N, const void* bias, const void* residual, long long ldr, const void* rowbias,
              int rows_per_group, long long ld_rowbias, int epi, void* Vt, int n_split, int heads, int hdim, int ntok,
-             float out_scale, int dtype, void* stream) {
+             float out_scale, int dtype, void* workspace, unsigned long long ws_bytes, void* stream) {
   if (!A || !B || !C || M <= 0 || N <= 0) return fail(CID_ERR_ARG, "cid_gemm: null pointer or empty problem (M=%d N=%d)", M, N);
+  if (int rc = check_ws(workspace, ws_bytes, "cid_gemm")) return rc;
   if (K1 <= 0 || K1 % 64 || K2 < 0 || K2 % 64) return fail(CID_ERR_ARG, "cid_gemm: K1=%d K2=%d must be multiples of 64", K1, K2);
   if (K2 > 0 && !A2) return fail(CID_ERR_ARG, "cid_gemm: K2 > 0 without A2");
   const int bn = cid_gemm_tile_n(N, epi);
@@ -396,30 +243,23 @@ int cid_gemm(const void* A, long long lda, const void* A2, long long lda2, int K
     return fail(CID_ERR_ARG, "cid_gemm: bad QKV epilogue arguments");
   CUtensorMap ta1, ta2, tb;
   int rc;
-  const bool v4 = use_v4(bn);
-  if (v4) {
-    if ((rc = map_3d_k(&ta1, A, K1, M, lda, 128))) return rc;
-    if (K2 > 0) { if ((rc = map_3d_k(&ta2, A2, K2, M, lda2, 128))) return rc; } else ta2 = ta1;
-    if ((rc = map_3d_k(&tb, B, K1 + K2, N, K1 + K2, bn))) return rc;
-  } else {
-    if ((rc = map_2d(&ta1, A, K1, M, lda, 128))) return rc;
-    if (K2 > 0) { if ((rc = map_2d(&ta2, A2, K2, M, lda2, 128))) return rc; } else ta2 = ta1;
-    if ((rc = map_2d(&tb, B, K1 + K2, N, K1 + K2, b_box_rows(bn)))) return rc;
-  }
+  if ((rc = map_2d(&ta1, A, K1, M, lda, 128))) return rc;
+  if (K2 > 0) { if ((rc = map_2d(&ta2, A2, K2, M, lda2, 128))) return rc; } else ta2 = ta1;
+  if ((rc = map_2d(&tb, B, K1 + K2, N, K1 + K2, bn))) return rc;
   GemmArgs g{};
   g.M = M; g.N = N; g.kblocks_a1 = K1 / 64; g.kblocks_a2 = K2 / 64; g.taps = 1; g.a_mode = A_GEMM;
   g.C = C; g.ldc = ldc; g.bias = bias; g.residual = residual; g.ldr = ldr;
   g.rowbias = rowbias; g.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; g.ld_rowbias = ld_rowbias;
   g.epi = epi; g.is_bf16 = dtype == CID_BF16; g.Vt = Vt; g.n_split = n_split; g.heads = heads; g.hdim = hdim; g.ntok = ntok;
   g.out_scale = out_scale;
-  if (v4) return dispatch_gemm4(bn, ta1, ta2, tb, g, (M + 127) / 128, static_cast<cudaStream_t>(stream));
-  return dispatch_gemm(bn, ta1, ta2, tb, g, (M + 127) / 128, static_cast<cudaStream_t>(stream));
+  return dispatch_gemm(bn, ta1, ta2, tb, g, (M + 127) / 128, workspace, (size_t)ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int cid_conv3x3(const void* X, const void* Wt, void* Y, long long ldy, int NB, int H, int W, int Cin, int Cout, int stride2,
                 const void* bias, const void* residual, long long ldr, const void* rowbias, long long ld_rowbias,
-                float out_scale, int dtype, void* stream) {
+                float out_scale, int dtype, void* workspace, unsigned long long ws_bytes, void* stream) {
   if (!X || !Wt || !Y || NB <= 0 || H <= 0 || W <= 0) return fail(CID_ERR_ARG, "cid_conv3x3: null pointer or empty problem");
+  if (int rc0 = check_ws(workspace, ws_bytes, "cid_conv3x3")) return rc0;
   if (Cin % 64 || Cout <= 0) return fail(CID_ERR_ARG, "cid_conv3x3: Cin=%d must be a multiple of 64", Cin);
   GemmArgs g{};
   if (W >= 128) { g.TW = 128; g.TH = 1; g.TN = 1; }
@@ -435,13 +275,7 @@ int cid_conv3x3(const void* X, const void* Wt, void* Y, long long ldy, int NB, i
   const int bn = cid_gemm_tile_n(Cout, CID_EPI_STORE);
   CUtensorMap ta, tb;
   int rc;
-  const bool v4 = use_v4(bn) && !stride2 && ((g.TW * g.TH * g.TN) % 8 == 0);
-  if (v4) {
-    cuuint64_t dims[5] = {64, cuuint64_t(W), cuuint64_t(H), cuuint64_t(NB), cuuint64_t(Cin / 64)};
-    cuuint64_t str[4] = {cuuint64_t(Cin) * 2, cuuint64_t(W) * Cin * 2, cuuint64_t(H) * W * Cin * 2, 128};
-    cuuint32_t box[5] = {64, cuuint32_t(g.TW), cuuint32_t(g.TH), cuuint32_t(g.TN), 2};
-    if ((rc = make_map(&ta, X, 5, dims, str, box))) return rc;
-  } else if (!stride2) {
+  if (!stride2) {
     cuuint64_t dims[4] = {cuuint64_t(Cin), cuuint64_t(W), cuuint64_t(H), cuuint64_t(NB)};
     cuuint64_t str[3] = {cuuint64_t(Cin) * 2, cuuint64_t(W) * Cin * 2, cuuint64_t(H) * W * Cin * 2};
     cuuint32_t box[4] = {64, cuuint32_t(g.TW), cuuint32_t(g.TH), cuuint32_t(g.TN)};
@@ -452,15 +286,13 @@ int cid_conv3x3(const void* X, const void* Wt, void* Y, long long ldy, int NB, i
     cuuint32_t box[5] = {64, cuuint32_t(g.TW), cuuint32_t(g.TH), 1, cuuint32_t(g.TN)};
     if ((rc = make_map(&ta, X, 5, dims, str, box))) return rc;
   }
-  if (v4) { if ((rc = map_3d_k(&tb, Wt, 9LL * Cin, Cout, 9LL * Cin, bn))) return rc; }
-  else if ((rc = map_2d(&tb, Wt, 9LL * Cin, Cout, 9LL * Cin, b_box_rows(bn)))) return rc;
+  if ((rc = map_2d(&tb, Wt, 9LL * Cin, Cout, 9LL * Cin, bn))) return rc;
   g.M = NB * H * W; g.N = Cout; g.kblocks_a1 = Cin / 64; g.kblocks_a2 = 0; g.taps = 9;
   g.a_mode = stride2 ? A_CONV_S2 : A_CONV; g.W = W; g.H = H; g.NB = NB;
   g.C = Y; g.ldc = ldy; g.bias = bias; g.residual = residual; g.ldr = ldr;
   g.rowbias = rowbias; g.rows_per_group = H * W; g.ld_rowbias = ld_rowbias;
   g.epi = EPI_STORE; g.is_bf16 = dtype == CID_BF16; g.out_scale = out_scale;
-  if (v4) return dispatch_gemm4(bn, ta, ta, tb, g, m_tiles, static_cast<cudaStream_t>(stream));
-  return dispatch_gemm(bn, ta, ta, tb, g, m_tiles, static_cast<cudaStream_t>(stream));
+  return dispatch_gemm(bn, ta, ta, tb, g, m_tiles, workspace, (size_t)ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int cid_attn_self(const void* Q, long long q_pitch, const void* K, long long k_pitch, const void* Vt, void* O, long long ldo,
@@ -474,41 +306,15 @@ int cid_attn_self(const void* Q, long long q_pitch, const void* K, long long k_p
   if ((rc = map_qk(&tk, K, B, N, H, d, k_pitch, 128))) return rc;
   AttnArgs a{}; a.B = B; a.H = H; a.Nq = N; a.Nkv = N; a.d = d; a.scale_log2 = 1.4426950408889634f / sqrtf(float(d));
   a.O = O; a.ldo = ldo; a.is_bf16 = dtype == CID_BF16;
-  if (false && attn_version() == 3 && N % 128 == 0) {   // DISABLED: one 4-D box for both 64-key chunks - no measured gain and two battery configs timed out
-    cuuint64_t dims[4] = {64, cuuint64_t(d), cuuint64_t(N / 64), cuuint64_t(B) * H};
-    cuuint64_t str[3] = {cuuint64_t(N) * 2, 128, cuuint64_t(N) * cuuint64_t(d) * 2};
-    cuuint32_t box[4] = {64, cuuint32_t(dp), 2, 1};
-    if ((rc = make_map(&tv, Vt, 4, dims, str, box))) return rc;
-    a.vt4d = 1;
-  } else if ((rc = map_vt(&tv, Vt, B * H, d, N, dp))) return rc;
+  if ((rc = map_vt(&tv, Vt, B * H, d, N, dp))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (attn_version() == 3) {
-    switch (dp) {
-      case 32: return launch_attn_self3<32>(tq, tk, tv, a, st);
-      case 48: return launch_attn_self3<48>(tq, tk, tv, a, st);
-      case 64: return launch_attn_self3<64>(tq, tk, tv, a, st);
-      case 80: return launch_attn_self3<80>(tq, tk, tv, a, st);
-      case 128: return launch_attn_self3<128>(tq, tk, tv, a, st);
-      case 160: return launch_attn_self3<160>(tq, tk, tv, a, st);
-    }
-  }
-  if (attn_version() == 2) {
-    switch (dp) {
-      case 32: return launch_attn_self2<32>(tq, tk, tv, a, st);
-      case 48: return launch_attn_self2<48>(tq, tk, tv, a, st);
-      case 64: return launch_attn_self2<64>(tq, tk, tv, a, st);
-      case 80: return launch_attn_self2<80>(tq, tk, tv, a, st);
-      case 128: return launch_attn_self2<128>(tq, tk, tv, a, st);
-      case 160: return launch_attn_self2<160>(tq, tk, tv, a, st);
-    }
-  }
   switch (dp) {
-    case 32: return launch_attn_self<32>(tq, tk, tv, a, st);
-    case 48: return launch_attn_self<48>(tq, tk, tv, a, st);
-    case 64: return launch_attn_self<64>(tq, tk, tv, a, st);
-    case 80: return launch_attn_self<80>(tq, tk, tv, a, st);
-    case 128: return launch_attn_self<128>(tq, tk, tv, a, st);
-    case 160: return launch_attn_self<160>(tq, tk, tv, a, st);
+    case 32: return launch_attn_self3<32>(tq, tk, tv, a, st);
+    case 48: return launch_attn_self3<48>(tq, tk, tv, a, st);
+    case 64: return launch_attn_self3<64>(tq, tk, tv, a, st);
+    case 80: return launch_attn_self3<80>(tq, tk, tv, a, st);
+    case 128: return launch_attn_self3<128>(tq, tk, tv, a, st);
+    case 160: return launch_attn_self3<160>(tq, tk, tv, a, st);
   }
   return fail(CID_ERR_UNSUPPORTED, "cid_attn_self: no instantiation for padded head dim %d", dp);
 }
@@ -649,20 +455,11 @@ int cid_skinny_linear(const void* x, long long ldx, const void* W, const void* b
                       int silu_in, int accumulate, int dtype, void* stream) {
   if (!x || !W || !y || K % 8 || K > 8192 || M <= 0) return fail(CID_ERR_ARG, "cid_skinny_linear: K=%d must be a multiple of 8 and <= 8192", K);
   const int slab = K <= 4096 ? 16 : 8;           // rows of x staged per pass: slab * K * 2 bytes of shared memory (<= 128 KB)
-  static bool configured = false;
-  if (!configured) {
-    int rc = set_smem(skinny_linear_kernel, 16 * 4096 * 2, "skinny_linear_kernel"); if (rc) return rc;
-    rc = set_smem(skinny_linear2_kernel, 16 * 4096 * 2, "skinny_linear2_kernel"); if (rc) return rc;
-    configured = true;
-  }
-  static const int version = env_int("CID_SKINNY_VERSION", 1);       // 2 = software-pipelined weight stream (elementwise.cuh)
-  if (version == 2)
-    skinny_linear2_kernel<<<(N + 7) / 8, 256, (size_t)slab * K * 2, static_cast<cudaStream_t>(stream)>>>(
-        (const uint16_t*)x, ldx, (const uint16_t*)W, (const uint16_t*)bias, (uint16_t*)y, ldy, M, N, K, silu_in, accumulate, dtype == CID_BF16, slab);
-  else
-    skinny_linear_kernel<<<(N + 7) / 8, 256, (size_t)slab * K * 2, static_cast<cudaStream_t>(stream)>>>(
-        (const uint16_t*)x, ldx, (const uint16_t*)W, (const uint16_t*)bias, (uint16_t*)y, ldy, M, N, K, silu_in, accumulate, dtype == CID_BF16, slab);
-  CID_CHECK_LAUNCH("skinny_linear_kernel");
+  static bool configured[MAX_DEVICES] = {};
+  if (int rc = set_smem(skinny_linear2_kernel, 16 * 4096 * 2, "skinny_linear2_kernel", configured)) return rc;
+  skinny_linear2_kernel<<<(N + 7) / 8, 256, (size_t)slab * K * 2, static_cast<cudaStream_t>(stream)>>>(
+      (const uint16_t*)x, ldx, (const uint16_t*)W, (const uint16_t*)bias, (uint16_t*)y, ldy, M, N, K, silu_in, accumulate, dtype == CID_BF16, slab);
+  CID_CHECK_LAUNCH("skinny_linear2_kernel");
   return 0;
 }
 int cid_cfg_sched_step(const void* eps, int ld_eps, float* x, float* x0_prev, void* x16, void* next_in, int CP, int B, int HW,
@@ -690,15 +487,8 @@ int cid_advance_step(int* step_dev, float* t_dev, const float* ts_table, int n, 
 
 int cid_set_splitk(int max_split, int min_kblocks) {
   if (max_split > 64) return fail(CID_ERR_ARG, "cid_set_splitk: max_split=%d > 64", max_split);
-  g_splitk_max = max_split;                                   // negative: back to CID_GEMM_SPLITK / the default
-  g_splitk_min_kb = min_kblocks == 0 ? 1 : min_kblocks;       // negative: back to CID_GEMM_SPLIT_MIN_KB / the default
-  return 0;
-}
-
-int cid_set_workspace(void* workspace, unsigned long long bytes) {
-  if (workspace == nullptr || bytes < WS_COUNTER_BYTES) { g_ws = nullptr; g_ws_bytes = 0; return 0; }
-  if (reinterpret_cast<uintptr_t>(workspace) % 256) return fail(CID_ERR_ARG, "cid_set_workspace: pointer must be 256-byte aligned");
-  g_ws = workspace; g_ws_bytes = (size_t)bytes;
+  g_splitk_max = max_split < 0 ? 4 : max_split;               // negative: back to the measured default; 0 / 1 disables splitting
+  g_splitk_min_kb = min_kblocks < 0 ? 48 : (min_kblocks == 0 ? 1 : min_kblocks);
   return 0;
 }
 

@@ -11,7 +11,7 @@
 //   * O and l are read once, at the end, for the normalisation.
 // The MMA warp also pre-computes its shared-memory descriptors (one IADD per MMA instead of a descriptor build).
 #pragma once
-#include "attn_tc2.cuh"
+#include "attn_common.cuh"
 
 namespace cid {
 

@@ -294,61 +294,9 @@ timestep_embed_kernel(const float* __restrict__ t_ptr, int t_stride, int rows, i
 }
 
 // y[M, N] (+)= act_in(x)[M, K] . W[N, K]^T + b     for tiny M (time-embedding MLPs, per-resnet temb projections, embedding producers)
-// act_in (argument silu_in): 0 identity, 1 SiLU, 2 GELU(erf)
-// one warp per output column; x staged in smem in 16-row slabs; W rows streamed with 16-byte loads.
-__global__ void __launch_bounds__(256)
-skinny_linear_kernel(const uint16_t* __restrict__ x, long long ldx, const uint16_t* __restrict__ w, const uint16_t* __restrict__ bias,
-                     uint16_t* __restrict__ y, long long ldy, int M, int N, int K, int silu_in, int accumulate, int bf, int slab) {
-  extern __shared__ uint16_t xs[];               // [slab][K], slab <= 16
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col = blockIdx.x * (blockDim.x >> 5) + warp;
-  for (int m0 = 0; m0 < M; m0 += slab) {
-    const int mrows = min(slab, M - m0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < mrows * K; i += blockDim.x) {
-      const int r = i / K, k = i % K;
-      float v = load16(x, (size_t)(m0 + r) * ldx + k, bf);
-      if (silu_in == 1) v = silu_f(v);
-      else if (silu_in == 2) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));   // exact-erf GELU (nn.GELU default)
-      store16(xs, (size_t)r * K + k, v, bf);
-    }
-    __syncthreads();
-    if (col < N) {
-      float acc[16];
-#pragma unroll
-      for (int r = 0; r < 16; ++r) acc[r] = 0.f;
-      for (int k = lane * 8; k < K; k += 256) {
-        float wf[8]; unpack8(*reinterpret_cast<const uint4*>(w + (size_t)col * K + k), wf, bf);
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          if (r < mrows) {
-            float xf[8]; unpack8(*reinterpret_cast<const uint4*>(xs + (size_t)r * K + k), xf, bf);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[r] += wf[e] * xf[e];
-          }
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < 16; ++r) {
-#pragma unroll
-        for (int o = 16; o; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
-      }
-      if (lane == 0) {
-        const float bv = bias ? load16(bias, col, bf) : 0.f;
-        for (int r = 0; r < mrows; ++r) {
-          float v = acc[r] + bv;
-          const size_t o = (size_t)(m0 + r) * ldy + col;
-          if (accumulate) v += load16(y, o, bf);
-          store16(y, o, v, bf);
-        }
-      }
-    }
-  }
-}
-
-// v2 of skinny_linear_kernel (same arguments, same math): the weight stream is software-pipelined - four 16-byte loads per lane are in
-// flight before the FMAs of the first one start - and x is staged with 16-byte copies instead of per-element index arithmetic.  The
-// embedding producers stream 250-600 MB of weights through this kernel on <= 10 rows, where v1 is bound by the load -> FMA dependency chain.
+// act_in: 0 identity, 1 SiLU, 2 GELU(erf).  One warp per output column; x staged in smem in 16-row slabs with 16-byte copies; the weight
+// stream is software-pipelined - four 16-byte loads per lane are in flight before the FMAs of the first one start (the embedding producers
+// stream 250-600 MB of weights through this kernel on <= 10 rows; the un-pipelined first version was bound by the load -> FMA chain).
 __global__ void __launch_bounds__(256)
 skinny_linear2_kernel(const uint16_t* __restrict__ x, long long ldx, const uint16_t* __restrict__ w, const uint16_t* __restrict__ bias,
                       uint16_t* __restrict__ y, long long ldy, int M, int N, int K, int act_in, int accumulate, int bf, int slab) {

@@ -1,4 +1,4 @@
-// Persistent tcgen05 GEMM / implicit-GEMM conv3x3 (v2 of gemm_tc.cuh; same arguments, same math).
+// Persistent tcgen05 GEMM / implicit-GEMM conv3x3 (arguments: gemm_common.cuh).
 //
 // One CTA per SM loops over output tiles (tile = blockIdx.x + i*gridDim.x, N-tile fastest so CTAs running at the same
 // time share the activation (A) tile in L2).  Roles (320 threads):
@@ -18,7 +18,7 @@
 #pragma once
 #include <type_traits>
 #include "elementwise.cuh"
-#include "gemm_tc.cuh"
+#include "gemm_common.cuh"
 
 namespace cid {
 

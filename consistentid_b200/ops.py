@@ -25,20 +25,22 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-# ---- GEMM tail-balancing workspace: one zero-filled buffer per process (one process per GPU), handed to the library once and kept alive
-_WORKSPACE = None
+# ---- GEMM tail-balancing workspace: one zero-filled buffer per DEVICE, owned here and passed to cid_gemm / cid_conv3x3 on every call
+# (the library keeps no pointer; include/cidb200.h "Workspace convention")
+_WORKSPACES = {}
 WORKSPACE_BYTES = 24 << 20
 
 
 def ensure_workspace(device=None):
-    """Give libcidb200 its split-K scratch (cid_set_workspace).  Idempotent; called by the engines and by ``gemm``/``conv3x3``."""
-    global _WORKSPACE
-    if _WORKSPACE is None:
-        _WORKSPACE = torch.zeros(WORKSPACE_BYTES, dtype=torch.uint8, device=device or torch.device("cuda", torch.cuda.current_device()))
-        rc = lib._lib.cid_set_workspace(_WORKSPACE.data_ptr(), WORKSPACE_BYTES)
-        if rc != 0:
-            raise lib.CidError(f"cid_set_workspace failed ({rc}): {lib.last_error()}")
-    return _WORKSPACE
+    """The split-K scratch tensor of ``device`` (allocated and zero-filled once; never under CUDA-graph capture: the engines call this at
+    construction)."""
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    ws = _WORKSPACES.get(dev.index)
+    if ws is None:
+        ws = _WORKSPACES[dev.index] = torch.zeros(WORKSPACE_BYTES, dtype=torch.uint8, device=dev)
+    return ws
 
 
 # ---- optional per-launch profiling (bench.py roofline pass): each tensor-core launch bracketed by CUDA events on the
@@ -89,12 +91,15 @@ def gemm(a, w, out, bias=None, residual=None, rowbias=None, rows_per_group=1, a2
     N = w.shape[0]
     assert w.shape[1] == K1 + K2 and w.is_contiguous()
     assert a.stride(1) == 1 and out.stride(1) == 1
-    if _WORKSPACE is None:
-        ensure_workspace(a.device)
+    for nm, t in (("w", w), ("out", out), ("a2", a2), ("bias", bias), ("residual", residual), ("rowbias", rowbias), ("vt", vt)):
+        if t is not None and t.dtype != a.dtype:      # the kernels read raw 16-bit words: a dtype mismatch would be silent garbage
+            raise TypeError(f"cid_gemm: {nm} is {t.dtype} but a is {a.dtype}")
+    ws = ensure_workspace(a.device)
     with _prof("gemm", 2.0 * M * N * (K1 + K2), 2.0 * (M * (K1 + K2) + N * (K1 + K2) + M * N), (M, N, K1 + K2, epi)):
         call("cid_gemm", _p(a), a.stride(0), _p(a2), 0 if a2 is None else a2.stride(0), K1, K2, _p(w), _p(out), out.stride(0),
              M, N, _p(bias), _p(residual), 0 if residual is None else residual.stride(0), _p(rowbias), rows_per_group,
-             0 if rowbias is None else rowbias.stride(0), epi, _p(vt), n_split, heads, hdim, ntok, float(out_scale), _dt(a), _stream())
+             0 if rowbias is None else rowbias.stride(0), epi, _p(vt), n_split, heads, hdim, ntok, float(out_scale), _dt(a),
+             ws.data_ptr(), WORKSPACE_BYTES, _stream())
     return out
 
 
@@ -102,12 +107,11 @@ def conv3x3(x, w, out, NB, H, W, Cin, Cout, bias=None, residual=None, rowbias=No
     """x: NHWC [NB,H,W,Cin] (or phase-split [NB,4,H,W,Cin] when stride2; H,W = output dims); w: [Cout, 9*Cin];
     out: [NB*H*W, >=Cout] rows."""
     M = NB * H * W
-    if _WORKSPACE is None:
-        ensure_workspace(x.device)
+    ws = ensure_workspace(x.device)
     with _prof("conv3x3", 2.0 * M * Cout * 9 * Cin, 2.0 * (M * Cin * (4 if stride2 else 1) + 9 * Cin * Cout + M * Cout), (M, Cout, 9 * Cin, 0)):
         call("cid_conv3x3", _p(x), _p(w), _p(out), out.stride(0), NB, H, W, Cin, Cout, 1 if stride2 else 0, _p(bias), _p(residual),
              0 if residual is None else residual.stride(0), _p(rowbias), 0 if rowbias is None else rowbias.stride(0),
-             float(out_scale), _dt(x), _stream())
+             float(out_scale), _dt(x), ws.data_ptr(), WORKSPACE_BYTES, _stream())
     return out
 
 
@@ -130,27 +134,32 @@ def pack_cross_kv(k_text, v_text, k_ip, v_ip, k_cat, vt_cat, B, C, heads, n_text
 
 
 def gn_stats(x1, C1, x2, C2, NB, HW, groups, sums, zero_sums=True):
-    call("cid_gn_stats", _p(x1), C1, _p(x2), C2, NB, HW, groups, _p(sums), 1 if zero_sums else 0, _dt(x1), _stream())
+    with _prof("gn_stats", 0.0, 2.0 * NB * HW * (C1 + C2)):                     # one read of the tensor
+        call("cid_gn_stats", _p(x1), C1, _p(x2), C2, NB, HW, groups, _p(sums), 1 if zero_sums else 0, _dt(x1), _stream())
 
 
 def gn_apply(x1, C1, x2, C2, NB, HW, groups, sums, gamma, beta, eps, silu, out, zero_next=None):
-    call("cid_gn_apply", _p(x1), C1, _p(x2), C2, NB, HW, groups, _p(sums), _p(gamma), _p(beta), float(eps), 1 if silu else 0,
-         _p(out), _p(zero_next), _dt(x1), _stream())
+    with _prof("gn_apply", 0.0, 4.0 * NB * HW * (C1 + C2)):                     # one read + one write
+        call("cid_gn_apply", _p(x1), C1, _p(x2), C2, NB, HW, groups, _p(sums), _p(gamma), _p(beta), float(eps), 1 if silu else 0,
+             _p(out), _p(zero_next), _dt(x1), _stream())
     return out
 
 
 def layernorm(x, gamma, beta, out, rows, C, eps=1e-5):
-    call("cid_layernorm", _p(x), _p(gamma), _p(beta), _p(out), rows, C, float(eps), _dt(x), _stream())
+    with _prof("layernorm", 0.0, 4.0 * rows * C):
+        call("cid_layernorm", _p(x), _p(gamma), _p(beta), _p(out), rows, C, float(eps), _dt(x), _stream())
     return out
 
 
 def upsample2x(x, out, NB, H, W, C):
-    call("cid_upsample2x", _p(x), _p(out), NB, H, W, C, _stream())
+    with _prof("upsample2x", 0.0, 2.0 * NB * H * W * C * 5):                    # read 1x, write 4x
+        call("cid_upsample2x", _p(x), _p(out), NB, H, W, C, _stream())
     return out
 
 
 def phase_split(x, out, NB, H, W, C):
-    call("cid_phase_split", _p(x), _p(out), NB, H, W, C, _stream())
+    with _prof("phase_split", 0.0, 4.0 * NB * H * W * C):
+        call("cid_phase_split", _p(x), _p(out), NB, H, W, C, _stream())
     return out
 
 
@@ -203,6 +212,12 @@ def perceiver_attn(q, kv, out, B, L, n_kv, heads, dim_head=64):
 
 
 def cfg_sched_step(eps, ld_eps, x, x0_prev, x16, next_in, CP, B, HW, guidance, coef_table, step_dev):
+    # eps 2 x 4 ch x 2 B read (a 16-byte sector per pixel is touched), x / x0 fp32 read + write, x16 write, next input 2 x 16 B write
+    with _prof("cfg_sched_step", 0.0, B * HW * (2 * 8 + 4 * 4 * 4 + 4 * 2 + (32 if next_in is not None else 0))):
+        return _cfg_sched_step(eps, ld_eps, x, x0_prev, x16, next_in, CP, B, HW, guidance, coef_table, step_dev)
+
+
+def _cfg_sched_step(eps, ld_eps, x, x0_prev, x16, next_in, CP, B, HW, guidance, coef_table, step_dev):
     call("cid_cfg_sched_step", _p(eps), ld_eps, _p(x), _p(x0_prev), _p(x16), _p(next_in), CP, B, HW, float(guidance),
          _p(coef_table), _p(step_dev), _dt(eps), _stream())
 

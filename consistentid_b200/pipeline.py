@@ -86,13 +86,15 @@ class B200Denoiser:
         HW, NB = h * w, 2 * B
         n = num_inference_steps
         nine = u.spec.in_channels == 9
-        sig = ("cn", B, h, w, n, float(guidance_scale), sch.kind, u.ip_scale, float(conditioning_scale), nine)
-        if sig != self._graph_sig:
-            self._graphs.clear()
-            self._graph_sig = sig
         u.plan(NB, h, w)
         controlnet.plan(B, h, w)
         controlnet.share_timestep(u)
+        # a captured graph bakes in buffer addresses (valid for one plan epoch of each engine), the key-row split and the dtype
+        sig = ("cn", B, h, w, n, float(guidance_scale), sch.kind, u.ip_scale, float(conditioning_scale), nine, u.plan_epoch, controlnet.plan_epoch,
+               id(controlnet), tuple(null_embeds.shape), tuple(text_embeds.shape), u.num_tokens, str(u.dtype))
+        if sig != self._graph_sig:
+            self._graphs.clear()
+            self._graph_sig = sig
         sch.set_timesteps(n, device=dev)
         coef, ts = sch.device_tables(dev)
         controlnet.set_control_image(control_image)
@@ -183,11 +185,13 @@ class B200Denoiser:
         HW, NB = h * w, 2 * B
         n = num_inference_steps
         sdxl = u.spec.addition_embed_type == "text_time"
-        sig = (B, h, w, n, float(guidance_scale), sch.kind, u.ip_scale)
+        u.plan(NB, h, w)
+        # a captured graph bakes in buffer addresses (valid for one plan epoch of the engine), the key-row split (n_text / n_ip) and the dtype
+        sig = (B, h, w, n, float(guidance_scale), sch.kind, u.ip_scale, u.plan_epoch, tuple(null_embeds.shape), tuple(text_embeds.shape),
+               tuple(augmented_embeds.shape), u.num_tokens, str(u.dtype))
         if sig != self._graph_sig:
             self._graphs.clear()
             self._graph_sig = sig
-        u.plan(NB, h, w)
         sch.set_timesteps(n, device=dev)
         coef, ts = sch.device_tables(dev)
         # ---- prompt phases (K/V caches + SDXL added-cond embedding), computed once per call

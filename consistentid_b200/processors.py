@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from . import ops
 from .lib import EPI_QKV
-from .weights import fold_lora
+from .weights import TensorIdent, fold_lora, same_tensors
 
 
 class LoRALinearLayer(nn.Module):
@@ -31,20 +31,20 @@ class LoRALinearLayer(nn.Module):
         nn.init.zeros_(self.up.weight)
 
 
-def _versions(*ts):
-    return tuple((t.data_ptr(), t._version) for t in ts)
+def _idents(*ts):
+    return tuple(TensorIdent(t) for t in ts)
 
 
 class _ProcessorBase(nn.Module):
     def _folded(self, tag, base_w, lora):
         """base_w + lora_scale * up @ down, cached until any of the three tensors is modified."""
-        key = _versions(base_w, lora.down.weight, lora.up.weight) + (self.lora_scale,)
+        srcs = (base_w, lora.down.weight, lora.up.weight)
         hit = self._cache.get(tag)
-        if hit is None or hit[0] != key:
+        if hit is None or hit[1] != self.lora_scale or not same_tensors(hit[0], srcs):
             w = fold_lora(base_w.detach(), lora.down.weight.detach().to(base_w.dtype), lora.up.weight.detach().to(base_w.dtype),
                           self.lora_scale, lora.network_alpha).contiguous()
-            self._cache[tag] = hit = (key, w)
-        return hit[1]
+            self._cache[tag] = hit = (_idents(*srcs), self.lora_scale, w)
+        return hit[2]
 
     @staticmethod
     def _prep(attn, hidden_states):
@@ -98,10 +98,10 @@ class Consistent_AttProcessor(_ProcessorBase):
         wq = self._folded("q", attn.to_q.weight, self.to_q_lora)
         wk = self._folded("k", attn.to_k.weight, self.to_k_lora)
         wv = self._folded("v", attn.to_v.weight, self.to_v_lora)
-        wkey = _versions(wq, wk, wv)
-        if self._cache.get("qkv_key") != wkey:
+        wkey = self._cache.get("qkv_key")                 # the folded weights are this object's own cache entries: identity is enough
+        if wkey is None or wkey[0] is not wq or wkey[1] is not wk or wkey[2] is not wv:
             self._cache["qkv"] = torch.cat([wq, wk, wv], 0).contiguous()
-            self._cache["qkv_key"] = wkey
+            self._cache["qkv_key"] = (wq, wk, wv)
         wo = self._folded("o", attn.to_out[0].weight, self.to_out_lora)
         x2 = x.view(M, C)
         qk = torch.empty((M, 2 * C), dtype=x.dtype, device=x.device)
@@ -148,9 +148,16 @@ class Consistent_IPAttProcessor(_ProcessorBase):
         wk = self._folded("k", attn.to_k.weight, self.to_k_lora)
         wv = self._folded("v", attn.to_v.weight, self.to_v_lora)
         wo = self._folded("o", attn.to_out[0].weight, self.to_out_lora)
-        # K/V depend only on the prompt: cached per (prompt tensor, weights) - recomputed when either changes
-        kv_key = _versions(ehs, wk, wv, self.to_k_ip.weight, self.to_v_ip.weight) + (tuple(ehs.shape),)
-        if self._cache.get("kv_key") != kv_key:
+        # K/V depend only on the prompt: cached per (prompt tensor OBJECT, weights).  The entry holds the prompt tensor itself, so a
+        # different prompt can never alias it through a recycled allocation; a loop that re-creates the prompt tensor every step (the
+        # reference's torch.cat at pipline_StableDiffusion_ConsistentID.py:542-549) recomputes K/V every step (4 small GEMMs + a pack).
+        for wt in (self.to_k_ip.weight, self.to_v_ip.weight):
+            if wt.dtype != x.dtype:
+                raise TypeError(f"to_k_ip / to_v_ip are {wt.dtype} but the activations are {x.dtype}: move the processor with .to(dtype) "
+                                "as the reference does (pipline_StableDiffusion_ConsistentID.py:166-172)")
+        kv_srcs = (ehs, self.to_k_ip.weight, self.to_v_ip.weight)
+        kv_hit = self._cache.get("kv_key")
+        if kv_hit is None or kv_hit[1] is not wk or kv_hit[2] is not wv or not same_tensors(kv_hit[0], kv_srcs):
             text = ehs[:, :n_text].reshape(B * n_text, cad).contiguous()
             ip = ehs[:, n_text:].reshape(B * n_ip, cad).contiguous()
             new = lambda r: torch.empty((r, C), dtype=x.dtype, device=x.device)
@@ -160,7 +167,7 @@ class Consistent_IPAttProcessor(_ProcessorBase):
             k_cat = torch.empty((B, 96, C), dtype=x.dtype, device=x.device)
             vt_cat = torch.empty((B * H, d, 96), dtype=x.dtype, device=x.device)
             ops.pack_cross_kv(kt, vt_, ki, vi, k_cat, vt_cat, B, C, H, n_text, n_ip)
-            self._cache["kv"], self._cache["kv_key"] = (k_cat, vt_cat), kv_key
+            self._cache["kv"], self._cache["kv_key"] = (k_cat, vt_cat), (_idents(*kv_srcs), wk, wv)
         k_cat, vt_cat = self._cache["kv"]
         q = torch.empty((M, C), dtype=x.dtype, device=x.device)
         ops.gemm(x.view(M, C), wq, q)

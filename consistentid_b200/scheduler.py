@@ -41,6 +41,10 @@ class B200Scheduler:
         self.num_inference_steps = n
         ratio = self.n_train // n
         ts = (np.arange(0, n) * ratio).round()[::-1].copy().astype(np.int64) + self.steps_offset
+        if self.kind == "dpmpp2m":
+            # diffusers 0.23 DPMSolverMultistepScheduler "leading" grid: n + 1 points, the last one dropped (961 ... 33 for n = 30)
+            r1 = self.n_train // (n + 1)
+            ts = (np.arange(0, n + 1) * r1).round()[::-1][:-1].copy().astype(np.int64) + self.steps_offset
         acp = self.acp
         coef = np.zeros((n, 8), dtype=np.float64)
         in_scale = np.ones(n + 1, dtype=np.float64)

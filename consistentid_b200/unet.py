@@ -21,7 +21,7 @@ import torch
 from . import lib, ops
 from .arch import UNetSpec, attn_processor_names, param_shapes, walk
 from .lib import EPI_GEGLU, EPI_QKV
-from .weights import fold_lora, interleave_geglu, pack_conv3x3
+from .weights import TensorIdent, fold_lora, interleave_geglu, pack_conv3x3, same_tensors
 
 N_TEXT_MAX, KROWS = 80, 96
 CIN_PAD = 64
@@ -165,6 +165,7 @@ class B200UNet:
         self._slots, self._ident, self._auto_next = {}, {}, 0
         self._graphs = {}
         self._gn_k = 0
+        self.plan_epoch = 0         # bumped whenever plan() drops the buffers: CUDA graphs captured against them are stale
         self._procs = {n: _EngineProcessor(self, n) for n in attn_processor_names(spec)}
 
     # ------------------------------------------------------------------ diffusers-facing surface
@@ -212,6 +213,7 @@ class B200UNet:
     def plan(self, NB, H, W):
         if self._plan != (NB, H, W):
             self._plan = (NB, H, W)
+            self.plan_epoch = getattr(self, "plan_epoch", 0) + 1
             self._kv.clear(); self._aug.clear(); self._graphs.clear(); self._slots.clear(); self._ident.clear()
             self._bufs = {k: v for k, v in self._bufs.items() if k[0] in ("t_dev",)}
             self._buf("x_in", (NB * H * W, CIN_PAD), zero=True)
@@ -227,17 +229,18 @@ class B200UNet:
         add = added_cond_kwargs or {}
         te, ti = add.get("text_embeds"), add.get("time_ids")
         if key is None:
-            # drop-in path: key on tensor identity (the reference loop re-creates the prompt tensor every step, in which case
-            # K/V are simply recomputed for that step); two rotating slots bound the memory
-            ident = (ehs.data_ptr(), ehs._version, tuple(ehs.shape), None if te is None else (te.data_ptr(), te._version),
-                     None if ti is None else (ti.data_ptr(), ti._version))
+            # drop-in path: the cache entry holds the keyed tensors themselves (weights.TensorIdent), so a later prompt can never alias
+            # an earlier one through a recycled allocation.  A loop that re-creates its prompt tensor every step (the reference's does:
+            # torch.cat at :542-549) therefore recomputes K/V every step - correct, ~5 small launches per attn2 layer; callers that
+            # want the per-prompt cache pass an explicit ``key`` (B200Denoiser does).  Two rotating slots bound the memory.
+            tensors = (ehs, te, ti)
             for k in ("auto:0", "auto:1"):
-                if self._ident.get(k) == ident and k in self._kv:
+                if k in self._kv and same_tensors(self._ident.get(k), tensors):
                     self._active_key = k
                     return k
             key = "auto:%d" % self._auto_next
             self._auto_next ^= 1
-            self._ident[key] = ident
+            self._ident[key] = tuple(None if t is None else TensorIdent(t) for t in tensors)
         slot = self._slots.setdefault(key, len(self._slots))
         assert ehs.shape[0] == NB and ehs.dtype == self.dtype, (ehs.shape, NB, ehs.dtype)
         L, cad = ehs.shape[1], ehs.shape[2]

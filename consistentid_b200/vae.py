@@ -30,8 +30,14 @@ class B200VAEDecoder:
     def __init__(self, state_dict, scaling_factor=0.18215, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
                  norm_num_groups=32, latent_channels=4, out_channels=3, dtype=torch.float16, device="cuda"):
         self.dtype, self.device = dtype, torch.device(device)
+        # AutoencoderKL config fields the pipelines read.  force_upcast is False: the SDXL pipeline's
+        # ``vae.dtype == float16 and vae.config.force_upcast`` branch (pipline_StableDiffusionXL_ConsistentID.py:669-675) must not try to
+        # ``.to(float32)`` this engine.  The fp32 score scaling here only removes the ATTENTION overflow; the real SDXL VAE weights also
+        # overflow fp16 in the resnet / upsample activations (that is why diffusers sets force_upcast), so decode SDXL latents with
+        # dtype=torch.bfloat16 (same exponent range as fp32) - parity has only been shown on synthetic weights.
         self.config = SimpleNamespace(scaling_factor=scaling_factor, block_out_channels=tuple(block_out_channels), layers_per_block=layers_per_block,
-                                      norm_num_groups=norm_num_groups, latent_channels=latent_channels, out_channels=out_channels)
+                                      norm_num_groups=norm_num_groups, latent_channels=latent_channels, out_channels=out_channels, in_channels=out_channels,
+                                      force_upcast=False, act_fn="silu", sample_size=512)
         self.groups = norm_num_groups
         ops.ensure_workspace(self.device)
         sd = {}

@@ -33,3 +33,44 @@ def pack_conv3x3(w: torch.Tensor, cin_pad: int | None = None) -> torch.Tensor:
     out = torch.zeros((cout, 3, 3, cp), dtype=w.dtype, device=w.device)
     out[..., :cin] = w.permute(0, 2, 3, 1)
     return out.reshape(cout, 9 * cp).contiguous()
+
+
+class TensorIdent:
+    """Identity of a tensor's CONTENT, for host-side caches keyed on "the same prompt / weight tensor as last time".
+
+    Keying on ``data_ptr()`` alone is wrong: the reference loop builds its prompt tensor with a fresh ``torch.cat`` every step
+    (pipline_StableDiffusion_ConsistentID.py:542-549), the caching allocator recycles freed blocks, and a DIFFERENT prompt can
+    land on the SAME address with version 0.  This object therefore holds a strong reference to the tensor that owns the storage
+    (so its address cannot be recycled while the cache entry lives) and matches only the same owner object, view geometry and
+    version counter.  Inference tensors (no version counter) never match: they are recomputed."""
+    __slots__ = ("base", "geom", "version")
+
+    def __init__(self, t):
+        self.base = t._base if t._base is not None else t
+        self.geom = (t.storage_offset(), tuple(t.shape), tuple(t.stride()), t.dtype)
+        try:
+            self.version = t._version
+        except RuntimeError:
+            self.version = None
+
+    def matches(self, t) -> bool:
+        if t is None or self.version is None:
+            return False
+        try:
+            v = t._version
+        except RuntimeError:
+            return False
+        base = t._base if t._base is not None else t
+        return base is self.base and v == self.version and (t.storage_offset(), tuple(t.shape), tuple(t.stride()), t.dtype) == self.geom
+
+
+def same_tensors(idents, tensors) -> bool:
+    """idents: tuple of TensorIdent | None recorded earlier; tensors: the tensors (or None) of this call."""
+    if idents is None or len(idents) != len(tensors):
+        return False
+    for i, t in zip(idents, tensors):
+        if (i is None) != (t is None):
+            return False
+        if i is not None and not i.matches(t):
+            return False
+    return True

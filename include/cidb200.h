@@ -27,12 +27,14 @@ typedef enum { CID_EPI_STORE = 0, CID_EPI_GEGLU = 1, CID_EPI_QKV = 2 } cid_epilo
 
 int cid_version(void);
 const char* cid_last_error(void);
-/* Scratch for the GEMM/conv tail balancing (split-K partial accumulators + arrival counters).  The library never allocates: the caller
- * hands it a ZERO-FILLED device buffer (>= 4 KB; 24 MB covers every shape) that stays valid and untouched by others until it is replaced
- * or cleared with (NULL, 0).  Without a workspace tiles are never split (same results, idle SMs in the last wave). */
-int cid_set_workspace(void* workspace, unsigned long long bytes);
-/* Tail-balancing policy: a tail tile is cut into at most max_split K-ranges of at least min_kblocks 64-wide k-blocks each (defaults 4 / 48,
- * or CID_GEMM_SPLITK / CID_GEMM_SPLIT_MIN_KB); max_split <= 1 disables splitting, negative values restore the defaults. */
+/* Workspace convention (cid_gemm / cid_conv3x3): `workspace` is caller-owned scratch for the tail balancing (split-K partial accumulators +
+ * arrival counters), passed PER CALL: a device buffer, 256-byte aligned, >= 4 KB (24 MB covers every shape of the SD / SDXL UNets), that the
+ * caller zero-fills ONCE before first use (the kernels re-arm the counters themselves) and does not share between streams that may run
+ * concurrently.  NULL / 0: tiles are never split (same results, idle SMs in the last wave).  The library keeps no pointer to it.
+ *
+ * Tail-balancing policy: a tail tile is cut into at most max_split K-ranges of at least min_kblocks 64-wide k-blocks each (defaults 4 / 48);
+ * max_split <= 1 disables splitting, negative values restore the defaults.  A process-wide POLICY knob, not state: results do not depend on it
+ * beyond fp32 summation order. */
 int cid_set_splitk(int max_split, int min_kblocks);
 /* N-tile width the GEMM will use for (N, epilogue): GEGLU weights must be row-interleaved per tile of this width. */
 int cid_gemm_tile_n(int N, int epi);
@@ -45,14 +47,14 @@ int cid_gemm_tile_n(int N, int epi);
 int cid_gemm(const void* A, long long lda, const void* A2, long long lda2, int K1, int K2, const void* B,
              void* C, long long ldc, int M, int N, const void* bias, const void* residual, long long ldr,
              const void* rowbias, int rows_per_group, long long ld_rowbias, int epi, void* Vt, int n_split, int heads,
-             int hdim, int ntok, float out_scale, int dtype, void* stream);
+             int hdim, int ntok, float out_scale, int dtype, void* workspace, unsigned long long ws_bytes, void* stream);
 
 /* 3x3 convolution, padding 1, as implicit GEMM over NHWC.  X: [NB,H,W,Cin] (stride 1) or the phase-split copy
  * [NB,4,H,W,Cin] of a [NB,2H,2W,Cin] tensor (stride2 = 1; H,W are OUTPUT dims).  Wt: [Cout, 9*Cin] = (ky,kx,c) order.
  * Y[NB*H*W, ldy].  Replaces ResnetBlock2D.conv1/conv2, Downsample2D.conv, Upsample2D.conv, conv_in, conv_out. */
 int cid_conv3x3(const void* X, const void* Wt, void* Y, long long ldy, int NB, int H, int W, int Cin, int Cout,
                 int stride2, const void* bias, const void* residual, long long ldr, const void* rowbias,
-                long long ld_rowbias, float out_scale, int dtype, void* stream);
+                long long ld_rowbias, float out_scale, int dtype, void* workspace, unsigned long long ws_bytes, void* stream);
 
 /* softmax(Q K^T / sqrt(d)) V per (sample, head).  Q,K: [B,N,H,d] views with row pitch q_pitch/k_pitch;
  * Vt: [B*H, d, N] (keys contiguous); O: [B,N,H*d] pitch ldo.  Replaces attention.py:152-159. */

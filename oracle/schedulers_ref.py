@@ -105,7 +105,9 @@ class DPMSolverPP2MRef(_Base):
 
     def set_timesteps(self, n, device=None):
         self.num_inference_steps = n
-        self.timesteps = torch.from_numpy(self._leading(n)).to(device)
+        # DPMSolverMultistepScheduler.set_timesteps, "leading": step_ratio = T // (n + 1); (arange(n + 1) * ratio).round()[::-1][:-1] + offset
+        r1 = self.n_train // (n + 1)
+        self.timesteps = torch.from_numpy((np.arange(0, n + 1) * r1).round()[::-1][:-1].copy().astype(np.int64) + self.steps_offset).to(device)
         a = self.alphas_cumprod
         self.alpha_t, self.sigma_t = a ** 0.5, (1 - a) ** 0.5
         self.lambda_t = torch.log(self.alpha_t) - torch.log(self.sigma_t)
