@@ -295,8 +295,19 @@ int cid_conv3x3(const void* X, const void* Wt, void* Y, long long ldy, int NB, i
   return dispatch_gemm(bn, ta, ta, tb, g, m_tiles, workspace, (size_t)ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
+static int attn_self_impl(const void* Q, long long q_pitch, const void* K, long long k_pitch, const void* Vt, void* O, long long ldo,
+                          int B, int H, int N, int n_valid, int d, int dtype, void* stream);
 int cid_attn_self(const void* Q, long long q_pitch, const void* K, long long k_pitch, const void* Vt, void* O, long long ldo,
                   int B, int H, int N, int d, int dtype, void* stream) {
+  return attn_self_impl(Q, q_pitch, K, k_pitch, Vt, O, ldo, B, H, N, N, d, dtype, stream);
+}
+int cid_attn_self_ragged(const void* Q, long long q_pitch, const void* K, long long k_pitch, const void* Vt, void* O, long long ldo,
+                         int B, int H, int N, int n_valid, int d, int dtype, void* stream) {
+  if (n_valid <= 0 || n_valid > N) return fail(CID_ERR_ARG, "cid_attn_self_ragged: need 0 < n_valid <= N (got %d, %d)", n_valid, N);
+  return attn_self_impl(Q, q_pitch, K, k_pitch, Vt, O, ldo, B, H, N, n_valid, d, dtype, stream);
+}
+static int attn_self_impl(const void* Q, long long q_pitch, const void* K, long long k_pitch, const void* Vt, void* O, long long ldo,
+                          int B, int H, int N, int n_valid, int d, int dtype, void* stream) {
   if (!Q || !K || !Vt || !O || B <= 0 || H <= 0 || N <= 0) return fail(CID_ERR_ARG, "cid_attn_self: null pointer or empty problem");
   const int dp = d_pad_for(d);
   if (dp < 0) return fail(CID_ERR_UNSUPPORTED, "cid_attn_self: head dim %d unsupported (multiple of 8, <= 160)", d);
@@ -304,7 +315,7 @@ int cid_attn_self(const void* Q, long long q_pitch, const void* K, long long k_p
   CUtensorMap tq, tk, tv; int rc;
   if ((rc = map_qk(&tq, Q, B, N, H, d, q_pitch, 128))) return rc;
   if ((rc = map_qk(&tk, K, B, N, H, d, k_pitch, 128))) return rc;
-  AttnArgs a{}; a.B = B; a.H = H; a.Nq = N; a.Nkv = N; a.d = d; a.scale_log2 = 1.4426950408889634f / sqrtf(float(d));
+  AttnArgs a{}; a.B = B; a.H = H; a.Nq = N; a.Nkv = n_valid; a.d = d; a.scale_log2 = 1.4426950408889634f / sqrtf(float(d));
   a.O = O; a.ldo = ldo; a.is_bf16 = dtype == CID_BF16;
   if ((rc = map_vt(&tv, Vt, B * H, d, N, dp))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

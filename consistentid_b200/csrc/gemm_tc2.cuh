@@ -393,6 +393,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] *= g.out_scale;
                 }
+                if (g.epi == EPI_GELU) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+                }
                 uint16_t* crow = reinterpret_cast<uint16_t*>(g.C) + grow * g.ldc + col0;
                 if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
                   float lo[8], hi[8];

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcidb200.so")
 
 F16, BF16 = 0, 1
-EPI_STORE, EPI_GEGLU, EPI_QKV = 0, 1, 2
+EPI_STORE, EPI_GEGLU, EPI_QKV, EPI_GELU = 0, 1, 2, 3
 
 
 class CidError(RuntimeError):
@@ -38,6 +38,7 @@ _SIGS = {
     "cid_gemm": ([_vp, _ll, _vp, _ll, _i, _i, _vp, _vp, _ll, _i, _i, _vp, _vp, _ll, _vp, _i, _ll, _i, _vp, _i, _i, _i, _i, _f, _i, _vp, C.c_ulonglong, _vp], _i),
     "cid_conv3x3": ([_vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _ll, _vp, _ll, _f, _i, _vp, C.c_ulonglong, _vp], _i),
     "cid_attn_self": ([_vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp], _i),
+    "cid_attn_self_ragged": ([_vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp], _i),
     "cid_attn_cross": ([_vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _f, _i, _vp], _i),
     "cid_pack_cross_kv": ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
     "cid_gn_stats": ([_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),

@@ -6,7 +6,7 @@ from __future__ import annotations
 import torch
 
 from . import lib
-from .lib import EPI_GEGLU, EPI_QKV, EPI_STORE, call
+from .lib import EPI_GEGLU, EPI_GELU, EPI_QKV, EPI_STORE, call
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -115,15 +115,19 @@ def conv3x3(x, w, out, NB, H, W, Cin, Cout, bias=None, residual=None, rowbias=No
     return out
 
 
-def attn_self(q, k, vt, out, B, H, N, d):
-    """q,k: views [B*N, >=H*d] (row pitch = stride(0)); vt: [B*H, d, N]; out: [B*N, H*d]."""
-    with _prof("attn_self", 4.0 * B * H * N * N * d, 2.0 * 4 * B * N * H * d):
-        call("cid_attn_self", _p(q), q.stride(0), _p(k), k.stride(0), _p(vt), _p(out), out.stride(0), B, H, N, d, _dt(q), _stream())
+def attn_self(q, k, vt, out, B, H, N, d, n_valid=None):
+    """q,k: views [B*N, >=H*d] (row pitch = stride(0)); vt: [B*H, d, N]; out: [B*N, H*d].  n_valid < N: keys >= n_valid are masked."""
+    nv = N if n_valid is None else n_valid
+    with _prof("attn_self", 4.0 * B * H * N * nv * d, 2.0 * 4 * B * N * H * d, ("B%d" % B, "H%d" % H, "N%d" % N, "d%d" % d)):
+        if nv == N:
+            call("cid_attn_self", _p(q), q.stride(0), _p(k), k.stride(0), _p(vt), _p(out), out.stride(0), B, H, N, d, _dt(q), _stream())
+        else:
+            call("cid_attn_self_ragged", _p(q), q.stride(0), _p(k), k.stride(0), _p(vt), _p(out), out.stride(0), B, H, N, nv, d, _dt(q), _stream())
     return out
 
 
 def attn_cross(q, k_cat, vt_cat, out, B, H, N, d, n_text, n_ip, ip_scale):
-    with _prof("attn_cross", 4.0 * B * H * N * (n_text + n_ip) * d, 2.0 * 2 * B * N * H * d):
+    with _prof("attn_cross", 4.0 * B * H * N * (n_text + n_ip) * d, 2.0 * 2 * B * N * H * d, ("B%d" % B, "H%d" % H, "N%d" % N, "d%d" % d)):
         call("cid_attn_cross", _p(q), q.stride(0), _p(k_cat), _p(vt_cat), _p(out), out.stride(0), B, H, N, d, n_text, n_ip,
              float(ip_scale), _dt(q), _stream())
     return out
@@ -134,19 +138,19 @@ def pack_cross_kv(k_text, v_text, k_ip, v_ip, k_cat, vt_cat, B, C, heads, n_text
 
 
 def gn_stats(x1, C1, x2, C2, NB, HW, groups, sums, zero_sums=True):
-    with _prof("gn_stats", 0.0, 2.0 * NB * HW * (C1 + C2)):                     # one read of the tensor
+    with _prof("gn_stats", 0.0, 2.0 * NB * HW * (C1 + C2), (NB * HW, C1 + C2)):                     # one read of the tensor
         call("cid_gn_stats", _p(x1), C1, _p(x2), C2, NB, HW, groups, _p(sums), 1 if zero_sums else 0, _dt(x1), _stream())
 
 
 def gn_apply(x1, C1, x2, C2, NB, HW, groups, sums, gamma, beta, eps, silu, out, zero_next=None):
-    with _prof("gn_apply", 0.0, 4.0 * NB * HW * (C1 + C2)):                     # one read + one write
+    with _prof("gn_apply", 0.0, 4.0 * NB * HW * (C1 + C2), (NB * HW, C1 + C2)):                     # one read + one write
         call("cid_gn_apply", _p(x1), C1, _p(x2), C2, NB, HW, groups, _p(sums), _p(gamma), _p(beta), float(eps), 1 if silu else 0,
              _p(out), _p(zero_next), _dt(x1), _stream())
     return out
 
 
 def layernorm(x, gamma, beta, out, rows, C, eps=1e-5):
-    with _prof("layernorm", 0.0, 4.0 * rows * C):
+    with _prof("layernorm", 0.0, 4.0 * rows * C, (rows, C)):
         call("cid_layernorm", _p(x), _p(gamma), _p(beta), _p(out), rows, C, float(eps), _dt(x), _stream())
     return out
 

@@ -75,7 +75,9 @@ class B200Denoiser:
     def controlnet_inpaint(self, controlnet, latents, null_embeds, augmented_embeds, text_embeds, control_image, image_latents,
                            noise, mask, num_inference_steps=50, guidance_scale=5.0, start_merge_step=0, conditioning_scale=1.0,
                            masked_image_latents=None):
-        """The reference's ControlNet + inpaint loop (pipelines/StableDIffusionControlNetInpaint_ConsistentID.py:375-449, strength 1):
+        """``controlnet`` None = the plain inpaint loop (pipelines/StableDIffusionInpaint_ConsistentID.py:305-359): same steps without the
+        ControlNet residuals; see ``inpaint``.
+        The reference's ControlNet + inpaint loop (pipelines/StableDIffusionControlNetInpaint_ConsistentID.py:375-449, strength 1):
         per step ControlNet on the cond half -> residuals into the UNet (both CFG halves) -> CFG + scheduler step -> for the
         4-channel UNet the latent blend with the re-noised original; a 9-channel UNet instead sees [latents | mask | masked latents].
         One CUDA-graph replay per step, like ``__call__``.  mask [B,1,h,w]: 1 = repaint."""
@@ -87,23 +89,27 @@ class B200Denoiser:
         n = num_inference_steps
         nine = u.spec.in_channels == 9
         u.plan(NB, h, w)
-        controlnet.plan(B, h, w)
-        controlnet.share_timestep(u)
+        if controlnet is not None:
+            controlnet.plan(B, h, w)
+            controlnet.share_timestep(u)
         # a captured graph bakes in buffer addresses (valid for one plan epoch of each engine), the key-row split and the dtype
-        sig = ("cn", B, h, w, n, float(guidance_scale), sch.kind, u.ip_scale, float(conditioning_scale), nine, u.plan_epoch, controlnet.plan_epoch,
-               id(controlnet), tuple(null_embeds.shape), tuple(text_embeds.shape), u.num_tokens, str(u.dtype))
+        sig = ("cn", B, h, w, n, float(guidance_scale), sch.kind, u.ip_scale, float(conditioning_scale), nine, u.plan_epoch,
+               None if controlnet is None else (id(controlnet), controlnet.plan_epoch),
+               tuple(null_embeds.shape), tuple(text_embeds.shape), u.num_tokens, str(u.dtype))
         if sig != self._graph_sig:
             self._graphs.clear()
             self._graph_sig = sig
         sch.set_timesteps(n, device=dev)
         coef, ts = sch.device_tables(dev)
-        controlnet.set_control_image(control_image)
+        if controlnet is not None:
+            controlnet.set_control_image(control_image)
         phases, cn_phases = {}, {}
         for name, pos in (("text", text_embeds), ("aug", augmented_embeds)):
             if (name == "text" and start_merge_step >= 0) or (name == "aug" and start_merge_step < n - 1):
                 phases[name] = u.set_prompt(self._pair(null_embeds, pos, B), None, key="phase:" + name)
-                pos16 = self._dev16(pos)
-                cn_phases[name] = controlnet.set_prompt(pos16.expand(B, *pos16.shape[1:]).contiguous(), None, key="phase:" + name)
+                if controlnet is not None:
+                    pos16 = self._dev16(pos)
+                    cn_phases[name] = controlnet.set_prompt(pos16.expand(B, *pos16.shape[1:]).contiguous(), None, key="phase:" + name)
         # add_noise coefficients of the NEXT timestep for the blend ((1, 0) after the last step)
         acp = sch.acp
         blend = np.zeros((n, 2), dtype=np.float32)
@@ -130,8 +136,11 @@ class B200Denoiser:
         ops.latents_to_input(st["x"], x_in, CIN_PAD, B, HW, coef, st["step"], n, keep_ch4_up=nine)
 
         def step_eager(phase):
-            down, mid = controlnet.forward(x_in[:B * HW], cn_phases[phase], conditioning_scale)
-            eps = u.forward(phases[phase], residuals=(down, mid))
+            if controlnet is not None:
+                down, mid = controlnet.forward(x_in[:B * HW], cn_phases[phase], conditioning_scale)
+                eps = u.forward(phases[phase], residuals=(down, mid))
+            else:
+                eps = u.forward(phases[phase])
             ops.cfg_sched_step(eps, 4, st["x"], st["x0"], st["x16"], None, CIN_PAD, B, HW, st["guidance"], coef, st["step"])
             if not nine:
                 ops.inpaint_blend(st["x"], st["x16"], st["img"], st["noise"], st["mask"], B, HW, st["blend"], st["step"])
@@ -168,6 +177,17 @@ class B200Denoiser:
         for i in range(n):
             run("text" if i <= start_merge_step else "aug")
         return st["x16"].reshape(B, 4, h, w).clone()
+
+    @torch.no_grad()
+    def inpaint(self, latents, null_embeds, augmented_embeds, text_embeds, image_latents, noise, mask, num_inference_steps=50,
+                guidance_scale=5.0, start_merge_step=0, masked_image_latents=None):
+        """The reference's plain inpaint loop (pipelines/StableDIffusionInpaint_ConsistentID.py:305-359, strength 1): UNet x 2B -> CFG ->
+        scheduler step -> for the 4-channel UNet ``latents = (1 - mask) * add_noise(image_latents, noise, t_next) + mask * latents``
+        (:340-352); a 9-channel inpaint UNet instead sees ``cat([latents, mask, masked_image_latents])`` every step (:320-321).
+        One CUDA-graph replay per step.  mask [B,1,h,w]: 1 = repaint."""
+        return self.controlnet_inpaint(None, latents, null_embeds, augmented_embeds, text_embeds, None, image_latents, noise, mask,
+                                       num_inference_steps=num_inference_steps, guidance_scale=guidance_scale, start_merge_step=start_merge_step,
+                                       masked_image_latents=masked_image_latents)
 
     # ------------------------------------------------------------------ public API
     @torch.no_grad()

@@ -23,7 +23,7 @@ extern "C" {
 
 typedef enum { CID_OK = 0, CID_ERR_ARG = -1, CID_ERR_CUDA = -2, CID_ERR_UNSUPPORTED = -3, CID_ERR_DRIVER = -4 } cid_status;
 typedef enum { CID_F16 = 0, CID_BF16 = 1 } cid_dtype;
-typedef enum { CID_EPI_STORE = 0, CID_EPI_GEGLU = 1, CID_EPI_QKV = 2 } cid_epilogue;
+typedef enum { CID_EPI_STORE = 0, CID_EPI_GEGLU = 1, CID_EPI_QKV = 2, CID_EPI_GELU = 3 } cid_epilogue;
 
 int cid_version(void);
 const char* cid_last_error(void);
@@ -43,7 +43,8 @@ int cid_gemm_tile_n(int N, int epi);
  * Replaces: attn.to_q/to_k/to_v/to_out (+ LoRA folded) attention.py:138-146,162,236-250,282; BasicTransformerBlock
  * GEGLU / FF linears, Transformer2D proj_in/out, ResnetBlock2D 1x1 conv_shortcut (diffusers 0.23).
  *   epi = GEGLU : B rows interleaved per tile (value half | gate half); writes C[M, N/2] = v * gelu(g).
- *   epi = QKV   : columns >= n_split are V and are written TRANSPOSED to Vt[(row/ntok)*heads + h, dd, row%ntok]. */
+ *   epi = QKV   : columns >= n_split are V and are written TRANSPOSED to Vt[(row/ntok)*heads + h, dd, row%ntok].
+ *   epi = GELU  : C = gelu_erf(acc + bias (+ residual)) - the fc1 + activation of the CLIP vision MLP. */
 int cid_gemm(const void* A, long long lda, const void* A2, long long lda2, int K1, int K2, const void* B,
              void* C, long long ldc, int M, int N, const void* bias, const void* residual, long long ldr,
              const void* rowbias, int rows_per_group, long long ld_rowbias, int epi, void* Vt, int n_split, int heads,
@@ -119,6 +120,12 @@ int cid_layernorm_rows(const void* x, long long ldx, long long x_group_rows, lon
  * q [B*L, ldq]; kv [B*n_kv, ldkv] = to_kv output (K columns [0,heads*64), V columns [heads*64, 2*heads*64)); out [B*L, ldo]. */
 int cid_perceiver_attn(const void* q, long long ldq, const void* kv, long long ldkv, void* out, long long ldo, int B, int L, int n_kv, int heads,
                        int dim_head, int dtype, void* stream);
+
+/* cid_attn_self on buffers of N tokens per sample (N % 8 == 0) of which only the first n_valid are real keys: the rest are masked out of the
+ * softmax (CLIP ViT-H/14: 257 tokens in 264-row buffers; transformers CLIPAttention behind
+ * pipline_StableDiffusion_ConsistentID.py:182-183, 202-203).  Rows >= n_valid of O are computed but meaningless. */
+int cid_attn_self_ragged(const void* Q, long long q_pitch, const void* K, long long k_pitch, const void* Vt, void* O, long long ldo,
+                         int B, int H, int N, int n_valid, int d, int dtype, void* stream);
 
 /* ---- VAE decode: everything but this reuses cid_conv3x3 / cid_gemm / cid_gn_* / cid_upsample2x ---- */
 /* In-place softmax over each row of x[rows, cols] (pitch ld), fp32 math: probabilities of the single-head d=512 attention of the VAE mid

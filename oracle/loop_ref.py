@@ -77,11 +77,13 @@ def denoise_controlnet_inpaint(unet, controlnet, scheduler, latents, null_embeds
         x_in = scheduler.scale_model_input(torch.cat([latents] * 2), t)
         cond = text_embeds if i <= start_merge_step else augmented_embeds
         ehs = torch.cat([null_embeds.expand(b, -1, -1), cond.expand(b, -1, -1)], dim=0)
-        c_in = scheduler.scale_model_input(latents, t)
-        down, mid = controlnet(c_in, t, encoder_hidden_states=cond.expand(b, -1, -1), controlnet_cond=control_image,
-                               conditioning_scale=conditioning_scale)
-        down2 = [torch.cat([d, d]) for d in down]
-        mid2 = torch.cat([mid, mid])
+        down2 = mid2 = None
+        if controlnet is not None:     # None = the plain inpaint loop, pipelines/StableDIffusionInpaint_ConsistentID.py:305-359
+            c_in = scheduler.scale_model_input(latents, t)
+            down, mid = controlnet(c_in, t, encoder_hidden_states=cond.expand(b, -1, -1), controlnet_cond=control_image,
+                                   conditioning_scale=conditioning_scale)
+            down2 = [torch.cat([d, d]) for d in down]
+            mid2 = torch.cat([mid, mid])
         if masked_image_latents is not None:
             x_in = torch.cat([x_in, torch.cat([mask] * 2), torch.cat([masked_image_latents] * 2)], dim=1)
         eps = unet(x_in, t, encoder_hidden_states=ehs, cross_attention_kwargs={}, down_block_additional_residuals=down2,
@@ -95,3 +97,12 @@ def denoise_controlnet_inpaint(unet, controlnet, scheduler, latents, null_embeds
                 proper = scheduler.add_noise(image_latents, noise, torch.tensor([int(ts[i + 1])]))
             latents = (1 - mask) * proper + mask * latents
     return latents
+
+
+def denoise_inpaint(unet, scheduler, latents, null_embeds, augmented_embeds, text_embeds, image_latents, noise, mask, num_inference_steps,
+                    guidance_scale=5.0, start_merge_step=0, masked_image_latents=None):
+    """pipelines/StableDIffusionInpaint_ConsistentID.py:305-359 (strength 1.0): the loop above without a ControlNet (9-channel concat :320-321,
+    4-channel latent blend :340-352)."""
+    return denoise_controlnet_inpaint(unet, None, scheduler, latents, null_embeds, augmented_embeds, text_embeds, None, image_latents, noise, mask,
+                                      num_inference_steps, guidance_scale=guidance_scale, start_merge_step=start_merge_step,
+                                      masked_image_latents=masked_image_latents)

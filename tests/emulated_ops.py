@@ -42,7 +42,10 @@ def gemm(a, w, out, bias=None, residual=None, rowbias=None, rows_per_group=1, a2
         return out
     if residual is not None:
         y = y + residual.float()
-    out.copy_(y * out_scale)
+    y = y * out_scale
+    if epi == 3:          # EPI_GELU
+        y = F.gelu(y)
+    out.copy_(y)
     return out
 
 
@@ -72,9 +75,10 @@ def _heads(t, B, N, H, d):
     return t.float().reshape(B, N, -1)[..., :H * d].reshape(B, N, H, d).transpose(1, 2)
 
 
-def attn_self(q, k, vt, out, B, H, N, d):
+def attn_self(q, k, vt, out, B, H, N, d, n_valid=None):
+    nv = N if n_valid is None else n_valid
     v = vt.float().view(B, H, d, N).transpose(2, 3)
-    o = F.scaled_dot_product_attention(_heads(q, B, N, H, d), _heads(k, B, N, H, d), v)
+    o = F.scaled_dot_product_attention(_heads(q, B, N, H, d), _heads(k, B, N, H, d)[:, :, :nv], v[:, :, :nv])
     out.copy_(o.transpose(1, 2).reshape(B * N, H * d))
     return out
 

@@ -158,6 +158,32 @@ def check_attn_self(B=2, H=2, N=256, d=64, dtype=torch.float16, seed=0):
     return _report(f"attn_self B{B} H{H} N{N} d{d} {str(dtype)[6:]}", out, ref, 1e-2)
 
 
+def check_attn_self_ragged(B=2, H=2, N=264, n_valid=257, d=80, dtype=torch.float16, seed=0):
+    """Buffers of N tokens, only the first n_valid are keys (CLIP ViT: 257 of 264)."""
+    ops = _ops()
+    C = H * d
+    q, k, v = (_rand((B, N, C), dtype, seed + i) for i in range(3))
+    vt = v.view(B, N, H, d).permute(0, 2, 3, 1).reshape(B * H, d, N).contiguous()
+    out = torch.empty((B * N, C), dtype=dtype, device=DEV)
+    ops.attn_self(q.view(B * N, C), k.view(B * N, C), vt, out, B, H, N, d, n_valid=n_valid)
+    torch.cuda.synchronize()
+    sp = lambda t: t.float().view(B, N, H, d).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(sp(q), sp(k)[:, :, :n_valid], sp(v)[:, :, :n_valid]).transpose(1, 2).reshape(B, N, C)
+    return _report(f"attn_self_ragged N{N} valid{n_valid} d{d}", out.view(B, N, C)[:, :n_valid].reshape(-1, C), ref[:, :n_valid].reshape(-1, C), 1e-2)
+
+
+def check_gemm_gelu(M=300, N=1280, K=320, dtype=torch.float16, seed=0):
+    """EPI_GELU: C = gelu_erf(A.B^T + bias) (CLIP MLP fc1)."""
+    from consistentid_b200.lib import EPI_GELU
+    ops = _ops()
+    a, w, b = _rand((M, K), dtype, seed), _rand((N, K), dtype, seed + 1, K ** -0.5), _rand((N,), dtype, seed + 2)
+    out = torch.empty((M, N), dtype=dtype, device=DEV)
+    ops.gemm(a, w, out, bias=b, epi=EPI_GELU)
+    torch.cuda.synchronize()
+    ref = F.gelu(a.float() @ w.float().t() + b.float())
+    return _report(f"gemm_gelu {M}x{N}x{K}", out, ref, 8e-3)
+
+
 def check_attn_cross(B=2, H=2, N=256, d=64, dtype=torch.float16, n_text=77, n_ip=4, ip_scale=1.0, seed=0):
     ops = _ops()
     C = H * d
@@ -422,6 +448,10 @@ CHECKS = {
     "attn_self_n64": (check_attn_self, dict(B=3, H=2, N=64, d=160)),
     "attn_self_n320": (check_attn_self, dict(B=1, H=2, N=320, d=64, dtype=B16)),
     "attn_self_n4096": (check_attn_self, dict(B=1, H=2, N=4096, d=40)),
+    "attn_self_ragged": (check_attn_self_ragged, dict(B=2, H=2, N=264, n_valid=257, d=80)),
+    "attn_self_ragged_small": (check_attn_self_ragged, dict(B=1, H=2, N=16, n_valid=10, d=64, dtype=B16)),
+    "gemm_gelu": (check_gemm_gelu, dict(M=300, N=1280, K=320)),
+    "gemm_gelu_5120": (check_gemm_gelu, dict(M=264, N=5120, K=1280, dtype=B16)),
     "attn_cross_d64": (check_attn_cross, dict(B=2, H=2, N=256, d=64)),
     "attn_cross_d40": (check_attn_cross, dict(B=2, H=8, N=1024, d=40, ip_scale=0.7)),
     "attn_cross_d80": (check_attn_cross, dict(B=1, H=4, N=200, d=80)),

@@ -81,3 +81,37 @@ def test_controlnet_inpaint_loop(nine):
                                  masked_image_latents=mil, **kw)
     torch.cuda.synchronize()
     _cmp(f"controlnet+inpaint loop nine={nine}", out, truth, eager)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nine", [False, True])
+def test_plain_inpaint_loop(nine):
+    """pipelines/StableDIffusionInpaint_ConsistentID.py:305-359: the inpaint loop WITHOUT a ControlNet (4-channel blend / 9-channel concat)."""
+    from consistentid_b200.pipeline import B200Denoiser
+    from consistentid_b200.scheduler import B200Scheduler
+    from oracle.loop_ref import denoise_inpaint
+    dtype = torch.float16
+    cfg = tiny_config("sd15")
+    if nine:
+        cfg.in_channels = 9
+    ref = synth.build_ref_unet(cfg, rank=16)
+    steps, B, h = 4, 2, cfg.sample_size
+    null, aug, txt = synth.synth_prompts(cfg.cross_attention_dim)
+    lat = synth.synth_latents(B, h, h, seed=0)
+    img, noise = synth.synth_latents(B, h, h, seed=7), synth.synth_latents(B, h, h, seed=8)
+    mask = torch.zeros(B, 1, h, h)
+    mask[:, :, h // 4: 3 * h // 4, h // 4: 3 * h // 4] = 1
+    mil = img * (1 - mask) if nine else None
+    kw = dict(guidance_scale=5.0, start_merge_step=1)
+    truth = denoise_inpaint(ref, make_scheduler("ddim"), lat, null, aug, txt, img, noise, mask, steps, masked_image_latents=mil, **kw)
+    c = lambda t_: None if t_ is None else t_.cuda().to(dtype)
+    ref16 = synth.build_ref_unet(cfg, rank=16, dtype=dtype).cuda()
+    for p in ref16.attn_processors.values():
+        p.cuda()
+    eager = denoise_inpaint(ref16, make_scheduler("ddim"), c(lat), c(null), c(aug), c(txt), c(img), c(noise), c(mask), steps,
+                            masked_image_latents=c(mil), **kw)
+    eng = _engine_from_oracle(ref, dtype, 16)
+    den = B200Denoiser(eng, B200Scheduler("ddim"), use_cuda_graph=True)
+    out = den.inpaint(lat, null, aug, txt, img, noise, mask, num_inference_steps=steps, masked_image_latents=mil, **kw)
+    torch.cuda.synchronize()
+    _cmp(f"plain inpaint loop nine={nine}", out, truth, eager)

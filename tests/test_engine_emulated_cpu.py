@@ -202,3 +202,77 @@ def test_processors_host_logic_against_reference_golden(emu, idx):
         _close("processor", got, want, 6e-2)
     p2.scale = 0.0
     assert (a2(x, encoder_hidden_states=ehs).float() - case["y_cross"]).abs().max().item() > 1e-3
+
+
+@pytest.mark.parametrize("nine", [False, True])
+def test_plain_inpaint_loop_host_logic(emu, nine):
+    """pipelines/StableDIffusionInpaint_ConsistentID.py:305-359 (no ControlNet): B200Denoiser.inpaint vs oracle.loop_ref.denoise_inpaint."""
+    from consistentid_b200.pipeline import B200Denoiser
+    from consistentid_b200.scheduler import B200Scheduler
+    from oracle.loop_ref import denoise_inpaint
+    cfg = tiny_config("sd15")
+    if nine:
+        cfg.in_channels = 9
+    ref = synth.build_ref_unet(cfg, rank=16)
+    steps, B, h = 3, 2, cfg.sample_size
+    null, aug, txt = synth.synth_prompts(cfg.cross_attention_dim)
+    lat = synth.synth_latents(B, h, h, seed=0)
+    img, noise = synth.synth_latents(B, h, h, seed=7), synth.synth_latents(B, h, h, seed=8)
+    mask = torch.zeros(B, 1, h, h)
+    mask[:, :, h // 4: 3 * h // 4, h // 4: 3 * h // 4] = 1
+    mil = img * (1 - mask) if nine else None
+    kw = dict(guidance_scale=5.0, start_merge_step=1)
+    want = denoise_inpaint(ref, make_scheduler("ddim"), lat, null, aug, txt, img, noise, mask, steps, masked_image_latents=mil, **kw)
+    den = B200Denoiser(_engine(ref), B200Scheduler("ddim"), use_cuda_graph=False)
+    got = den.inpaint(lat, null, aug, txt, img, noise, mask, num_inference_steps=steps, masked_image_latents=mil, **kw)
+    _close(f"plain inpaint loop nine={nine}", got, want, 5e-4)
+
+
+def test_clip_vision_encoder_host_logic(emu):
+    """consistentid_b200/clip.py on emulated kernels vs oracle/clip_ref.py (pinned on transformers): weight packing, the 264-row
+    padded token buffers with masked pad keys, layer count (hidden_states[-2] skips the last layer)."""
+    from consistentid_b200.clip import B200CLIPVisionEncoder
+    from oracle import clip_ref
+    from tests.test_clip_gpu import _weights
+    C, heads, layers, inter, image = 128, 2, 3, 256, 42
+    sd = _weights(C, heads, layers, inter, image, 14)
+    x = torch.randn(2, 3, image, image, generator=torch.Generator().manual_seed(5))
+    want = clip_ref.penultimate_hidden_state(sd, x, heads)
+    enc = B200CLIPVisionEncoder(sd, num_attention_heads=heads, dtype=torch.float32, device="cpu")
+    got = enc(x)
+    assert got.shape == want.shape
+    _close("clip vision encoder", got, want, 2e-4)
+
+
+def test_prompt_cache_never_aliases_a_recycled_allocation(emu):
+    """the drop-in ``unet(...)`` path keys its K/V cache on the prompt TENSOR.  A reference-style loop builds a fresh prompt
+    tensor every step; once the old one is freed the allocator may hand the same address to a DIFFERENT prompt.  The cache entry must hold the
+    keyed tensor (so that cannot happen) and must miss for a new tensor object even if it had the same address, shape and version."""
+    cfg = tiny_config("sd15")
+    ref = synth.build_ref_unet(cfg, rank=16)
+    B, h = 1, cfg.sample_size
+    null, aug, txt = synth.synth_prompts(cfg.cross_attention_dim)
+    x = synth.synth_latents(2 * B, h, h, seed=3)
+    t = torch.tensor(601)
+    eng = _engine(ref)
+    with torch.no_grad():
+        want_txt = ref(x, t, torch.cat([null, txt])).sample
+        want_aug = ref(x, t, torch.cat([null, aug])).sample
+    # reference-style loop: fresh torch.cat per step, alternating contents, previous tensors dropped
+    for step in range(4):
+        ehs = torch.cat([null, txt if step % 2 == 0 else aug])
+        got = eng(x, t, ehs, cross_attention_kwargs={}).sample
+        _close(f"step {step}", got, want_txt if step % 2 == 0 else want_aug, 2e-4)
+        del ehs
+    # the same tensor OBJECT twice hits the cache; an in-place edit (version bump) misses it
+    ehs = torch.cat([null, txt])
+    eng(x, t, ehs, cross_attention_kwargs={})
+    key = eng._active_key
+    eng(x, t, ehs, cross_attention_kwargs={})
+    assert eng._active_key == key
+    ehs.copy_(torch.cat([null, aug]))
+    got = eng(x, t, ehs, cross_attention_kwargs={}).sample
+    _close("after in-place edit", got, want_aug, 2e-4)
+    # the cache entries hold the keyed tensors alive
+    from consistentid_b200.weights import TensorIdent
+    assert all(isinstance(i, TensorIdent) for ids in eng._ident.values() for i in ids if i is not None)

@@ -27,21 +27,25 @@ kw = dict(guidance_scale=wl["guidance"], start_merge_step=-1, **{k: v.to(dev) fo
 args = (lat.to(dev), prompts[0].to(dev), prompts[1].to(dev), prompts[2].to(dev))
 den(*args, num_inference_steps=2, **kw)
 agg = collections.OrderedDict()
-for rep in range(3):
+REPS = 3
+for rep in range(REPS):
     den(*args, num_inference_steps=1, profile=True, **kw)
     for r in den.last_profile:
-        a = agg.setdefault((r["kind"], r["shape"]), [0, 0.0, r["flops"]])
-        a[0] += 1; a[1] += r["ms"]
-tot = sum(a[1] for a in agg.values()) / 3
-print(f"{wl_name}: tensor-core launches of one iteration: {tot:.3f} ms")
-print(f"{'kind':9s} {'M':>6s} {'N':>6s} {'K':>6s} epi   n   ms/iter   TF/s  tiles waves eff")
-for (kind, sh), (n, ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    n //= 3; ms /= 3
-    if sh is None or kind not in ("gemm", "conv3x3"):
-        print(f"{kind:9s} {'':27s} {n:3d} {ms:8.3f} {fl * n / ms / 1e9:7.1f}")
+        a = agg.setdefault((r["kind"], r["shape"]), [0, 0.0, 0.0, 0.0])
+        a[0] += 1; a[1] += r["ms"]; a[2] += r["flops"]; a[3] += r["bytes"]
+tot = sum(a[1] for a in agg.values()) / REPS
+print(f"{wl_name}: profiled launches of one iteration: {tot:.3f} ms (CUDA events per launch, eager, no PDL overlap)")
+print(f"{'kind':14s} {'M':>6s} {'N':>6s} {'K':>6s} epi   n   ms/iter   TF/s    GB/s  tiles waves eff")
+for (kind, sh), (n, ms, fl, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    n //= REPS; ms /= REPS; fl /= REPS; by /= REPS
+    tf = fl / ms / 1e9 if fl else 0.0
+    gbs = by / ms / 1e6
+    if kind not in ("gemm", "conv3x3"):
+        desc = "" if sh is None else "x".join(str(v) for v in sh)
+        print(f"{kind:14s} {desc:27s} {n:3d} {ms:8.3f} {tf:7.1f} {gbs:7.0f}")
         continue
     M, N, K, epi = sh
     bn = lib.gemm_tile_n(N, epi)
     tiles = math.ceil(M / 128) * math.ceil(N / bn)
     waves = tiles / 148
-    print(f"{kind:9s} {M:6d} {N:6d} {K:6d} {epi:3d} {n:3d} {ms:8.3f} {fl * n / ms / 1e9:7.1f} {tiles:6d} {waves:5.2f} {waves / math.ceil(waves):4.2f}  BN={bn}")
+    print(f"{kind:14s} {M:6d} {N:6d} {K:6d} {epi:3d} {n:3d} {ms:8.3f} {tf:7.1f} {gbs:7.0f} {tiles:6d} {waves:5.2f} {waves / math.ceil(waves):4.2f}  BN={bn}")
