@@ -12,7 +12,11 @@
 
 #include "../../include/cidb200.h"
 #include "attn_cross.cuh"
-#include "attn_tc3.cuh"
+#ifdef CID_ATTN_V3
+#include "attn_tc3.cuh"          // A/B builds only (tools/build_variant.sh): the round-1 kernel
+#else
+#include "attn_tc4.cuh"
+#endif
 #include "elementwise.cuh"
 #include "embed.cuh"
 #include "gemm_tc2.cuh"
@@ -173,8 +177,9 @@ int d_pad_for(int d) {
   return -1;
 }
 
+#ifdef CID_ATTN_V3
 template <int D_PAD>
-int launch_attn_self3(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
+int launch_attn_self(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
   using C = Attn2Cfg<D_PAD>;
   static bool configured[MAX_DEVICES] = {};
   if (int rc = set_smem(attn_self3_kernel<D_PAD>, C::TOTAL, "attn_self3_kernel", configured)) return rc;
@@ -183,6 +188,22 @@ int launch_attn_self3(const CUtensorMap& q, const CUtensorMap& k, const CUtensor
   CID_CHECK_LAUNCH("attn_self3_kernel");
   return 0;
 }
+#else
+template <int D_PAD, int BF>
+int launch_attn_self_t(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
+  using C = Attn2Cfg<D_PAD>;
+  static bool configured[MAX_DEVICES] = {};
+  if (int rc = set_smem(attn_self4_kernel<D_PAD, BF>, C::TOTAL, "attn_self4_kernel", configured)) return rc;
+  dim3 grid((a.Nq + 127) / 128, a.H, a.B);
+  launch_pdl(attn_self4_kernel<D_PAD, BF>, dim3(grid), dim3(ATTN_THREADS), C::TOTAL, st, q, k, v, a);
+  CID_CHECK_LAUNCH("attn_self4_kernel");
+  return 0;
+}
+template <int D_PAD>
+int launch_attn_self(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
+  return a.is_bf16 ? launch_attn_self_t<D_PAD, 1>(q, k, v, a, st) : launch_attn_self_t<D_PAD, 0>(q, k, v, a, st);
+}
+#endif
 template <int D_PAD>
 int launch_attn_cross(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
   using C = CrossCfg<D_PAD>;
@@ -320,12 +341,12 @@ static int attn_self_impl(const void* Q, long long q_pitch, const void* K, long 
   if ((rc = map_vt(&tv, Vt, B * H, d, N, dp))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (dp) {
-    case 32: return launch_attn_self3<32>(tq, tk, tv, a, st);
-    case 48: return launch_attn_self3<48>(tq, tk, tv, a, st);
-    case 64: return launch_attn_self3<64>(tq, tk, tv, a, st);
-    case 80: return launch_attn_self3<80>(tq, tk, tv, a, st);
-    case 128: return launch_attn_self3<128>(tq, tk, tv, a, st);
-    case 160: return launch_attn_self3<160>(tq, tk, tv, a, st);
+    case 32: return launch_attn_self<32>(tq, tk, tv, a, st);
+    case 48: return launch_attn_self<48>(tq, tk, tv, a, st);
+    case 64: return launch_attn_self<64>(tq, tk, tv, a, st);
+    case 80: return launch_attn_self<80>(tq, tk, tv, a, st);
+    case 128: return launch_attn_self<128>(tq, tk, tv, a, st);
+    case 160: return launch_attn_self<160>(tq, tk, tv, a, st);
   }
   return fail(CID_ERR_UNSUPPORTED, "cid_attn_self: no instantiation for padded head dim %d", dp);
 }

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcidb200.so")
+LIB_PATH = os.environ.get("CID_LIB_PATH") or os.path.join(_HERE, "libcidb200.so")     # CID_LIB_PATH: A/B builds of the same ABI (tools/build_variant.sh)
 
 F16, BF16 = 0, 1
 EPI_STORE, EPI_GEGLU, EPI_QKV, EPI_GELU = 0, 1, 2, 3
