@@ -109,12 +109,14 @@ class B200ControlNet(B200UNet):
         spec, P, buf = self.spec, self.params, self._buf
         kv = self._kv[key]
         self._gn_k = 0
+        self._stats_begin()
         cond, cb, ch, cw = self._cond
         assert (cb, ch, cw) == (NB, H, W), ("control image does not match the latent batch/resolution", (cb, ch, cw), (NB, H, W))
         emb, temb_all = self._time_embedding(key)
         c0 = spec.block_out_channels[0]
         x = buf("h.conv_in", (NB * H * W, c0))
-        ops.conv3x3(x_in_rows, P["conv_in.w"], x, NB, H, W, CIN_PAD, c0, bias=P["conv_in.b"], residual=cond)
+        ops.conv3x3(x_in_rows, P["conv_in.w"], x, NB, H, W, CIN_PAD, c0, bias=P["conv_in.b"], residual=cond,
+                    chan_stats=self._stats_slot(x, H * W, c0))
         skips = [(x, c0)]
         h, w = H, W
         for kind, i, layers, has_sampler in walk(spec):
@@ -138,6 +140,7 @@ class B200ControlNet(B200UNet):
             down.append(o)
         mid = buf("zero_out.mid", tuple(x.shape))
         ops.gemm(x, P["zero.mid.w"], mid, bias=P["zero.mid.b"], out_scale=conditioning_scale)
+        self._stats_used = self._stats_off
         return down, mid
 
     def __call__(self, sample, timestep, encoder_hidden_states, controlnet_cond, conditioning_scale=1.0, return_dict=False, **_):

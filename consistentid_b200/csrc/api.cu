@@ -117,12 +117,12 @@ int num_sms() {
 constexpr size_t WS_COUNTER_BYTES = 4096;
 int g_splitk_min_kb = 48, g_splitk_max = 4;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI, int BF>
 int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, void* ws, size_t ws_bytes,
                  cudaStream_t st) {
   using SM = Gemm2Smem<BN, STAGES>;
   static bool configured[MAX_DEVICES] = {};
-  if (int rc = set_smem(gemm_tc2_kernel<BN, STAGES>, SM::TOTAL, "gemm_tc2_kernel", configured)) return rc;
+  if (int rc = set_smem(gemm_tc2_kernel<BN, STAGES, EPI, BF>, SM::TOTAL, "gemm_tc2_kernel", configured)) return rc;
   const int n_tiles = (g.N + BN - 1) / BN;
   const int total = n_tiles * m_tiles;
   const int G = num_sms();
@@ -145,18 +145,33 @@ int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap
       if (sched.tail_tiles * sp > grid) grid = sched.tail_tiles * sp;
     }
   }
-  launch_pdl(gemm_tc2_kernel<BN, STAGES>, dim3(grid), dim3(GEMM2_THREADS), SM::TOTAL, st, a1, a2, b, g, n_tiles, sched);
+  launch_pdl(gemm_tc2_kernel<BN, STAGES, EPI, BF>, dim3(grid), dim3(GEMM2_THREADS), SM::TOTAL, st, a1, a2, b, g, n_tiles, sched);
   CID_CHECK_LAUNCH("gemm_tc2_kernel");
   return 0;
+}
+template <int BN, int STAGES>
+int launch_gemm2_any(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  const int flavour = g.epi == EPI_GEGLU ? EPI_GEGLU : (g.epi == EPI_QKV ? EPI_QKV : EPI_STORE);      // EPI_GELU rides on the store flavour
+#define CID_G2(E) (g.is_bf16 ? launch_gemm2<BN, STAGES, E, 1>(a1, a2, b, g, m_tiles, ws, ws_bytes, st) \
+                             : launch_gemm2<BN, STAGES, E, 0>(a1, a2, b, g, m_tiles, ws, ws_bytes, st))
+  if constexpr (BN >= 32) {
+    if (flavour == EPI_GEGLU) return CID_G2(EPI_GEGLU);
+    if (flavour == EPI_QKV) return CID_G2(EPI_QKV);
+  } else {
+    if (flavour != EPI_STORE) return fail(CID_ERR_UNSUPPORTED, "GEGLU / QKV epilogues need an N tile >= 32");
+  }
+  return CID_G2(EPI_STORE);
+#undef CID_G2
 }
 
 int dispatch_gemm(int bn, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, void* ws,
                   size_t ws_bytes, cudaStream_t st) {
   switch (bn) {
-    case 256: return launch_gemm2<256, 4>(a1, a2, b, g, m_tiles, ws, ws_bytes, st);
-    case 160: return launch_gemm2<160, 5>(a1, a2, b, g, m_tiles, ws, ws_bytes, st);
-    case 64: return launch_gemm2<64, 8>(a1, a2, b, g, m_tiles, ws, ws_bytes, st);
-    case 16: return launch_gemm2<16, 8>(a1, a2, b, g, m_tiles, ws, ws_bytes, st);
+    case 256: return launch_gemm2_any<256, 4>(a1, a2, b, g, m_tiles, ws, ws_bytes, st);
+    case 160: return launch_gemm2_any<160, 5>(a1, a2, b, g, m_tiles, ws, ws_bytes, st);
+    case 64: return launch_gemm2_any<64, 8>(a1, a2, b, g, m_tiles, ws, ws_bytes, st);
+    case 16: return launch_gemm2_any<16, 8>(a1, a2, b, g, m_tiles, ws, ws_bytes, st);
   }
   return fail(CID_ERR_UNSUPPORTED, "no GEMM instantiation for tile N %d", bn);
 }
@@ -253,8 +268,10 @@ int cid_gemm_tile_n(int N, int epi) {
 int cid_gemm(const void* A, long long lda, const void* A2, long long lda2, int K1, int K2, const void* B, void* C,
              long long ldc, int M, int N, const void* bias, const void* residual, long long ldr, const void* rowbias,
              int rows_per_group, long long ld_rowbias, int epi, void* Vt, int n_split, int heads, int hdim, int ntok,
-             float out_scale, int dtype, void* workspace, unsigned long long ws_bytes, void* stream) {
+             float out_scale, int dtype, void* workspace, unsigned long long ws_bytes, float* chan_stats, int stats_rows, void* stream) {
   if (!A || !B || !C || M <= 0 || N <= 0) return fail(CID_ERR_ARG, "cid_gemm: null pointer or empty problem (M=%d N=%d)", M, N);
+  if (chan_stats && (epi != CID_EPI_STORE || stats_rows <= 0 || stats_rows % 128 || M % stats_rows))
+    return fail(CID_ERR_ARG, "cid_gemm: fused statistics need the plain store epilogue and stats_rows (%d) a multiple of 128 dividing M", stats_rows);
   if (int rc = check_ws(workspace, ws_bytes, "cid_gemm")) return rc;
   if (K1 <= 0 || K1 % 64 || K2 < 0 || K2 % 64) return fail(CID_ERR_ARG, "cid_gemm: K1=%d K2=%d must be multiples of 64", K1, K2);
   if (K2 > 0 && !A2) return fail(CID_ERR_ARG, "cid_gemm: K2 > 0 without A2");
@@ -272,13 +289,13 @@ int cid_gemm(const void* A, long long lda, const void* A2, long long lda2, int K
   g.C = C; g.ldc = ldc; g.bias = bias; g.residual = residual; g.ldr = ldr;
   g.rowbias = rowbias; g.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; g.ld_rowbias = ld_rowbias;
   g.epi = epi; g.is_bf16 = dtype == CID_BF16; g.Vt = Vt; g.n_split = n_split; g.heads = heads; g.hdim = hdim; g.ntok = ntok;
-  g.out_scale = out_scale;
+  g.out_scale = out_scale; g.chan_stats = chan_stats; g.stats_rows = stats_rows;
   return dispatch_gemm(bn, ta1, ta2, tb, g, (M + 127) / 128, workspace, (size_t)ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int cid_conv3x3(const void* X, const void* Wt, void* Y, long long ldy, int NB, int H, int W, int Cin, int Cout, int stride2,
                 const void* bias, const void* residual, long long ldr, const void* rowbias, long long ld_rowbias,
-                float out_scale, int dtype, void* workspace, unsigned long long ws_bytes, void* stream) {
+                float out_scale, int dtype, void* workspace, unsigned long long ws_bytes, float* chan_stats, void* stream) {
   if (!X || !Wt || !Y || NB <= 0 || H <= 0 || W <= 0) return fail(CID_ERR_ARG, "cid_conv3x3: null pointer or empty problem");
   if (int rc0 = check_ws(workspace, ws_bytes, "cid_conv3x3")) return rc0;
   if (Cin % 64 || Cout <= 0) return fail(CID_ERR_ARG, "cid_conv3x3: Cin=%d must be a multiple of 64", Cin);
@@ -313,6 +330,10 @@ int cid_conv3x3(const void* X, const void* Wt, void* Y, long long ldy, int NB, i
   g.C = Y; g.ldc = ldy; g.bias = bias; g.residual = residual; g.ldr = ldr;
   g.rowbias = rowbias; g.rows_per_group = H * W; g.ld_rowbias = ld_rowbias;
   g.epi = EPI_STORE; g.is_bf16 = dtype == CID_BF16; g.out_scale = out_scale;
+  if (chan_stats) {
+    if (g.TN != 1) return fail(CID_ERR_UNSUPPORTED, "cid_conv3x3: fused statistics need every 128-pixel tile inside one sample (H*W = %d too small)", H * W);
+    g.chan_stats = chan_stats; g.stats_rows = H * W;
+  }
   return dispatch_gemm(bn, ta, ta, tb, g, m_tiles, workspace, (size_t)ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
@@ -415,6 +436,19 @@ int cid_gn_apply(const void* x1, int C1, const void* x2, int C2, int NB, int HW,
              (const uint16_t*)x1, C1, (const uint16_t*)x2, C2, HW, groups, sums, (const uint16_t*)gamma, (const uint16_t*)beta, eps, silu,
              (uint16_t*)y, zero_next, int(dtype == CID_BF16));
   CID_CHECK_LAUNCH("gn_apply_kernel");
+  return 0;
+}
+int cid_gn_apply_ch(const void* x1, int C1, const float* sums1, const void* x2, int C2, const float* sums2, int NB, int HW, int groups,
+                    const void* gamma, const void* beta, float eps, int silu, void* y, int dtype, void* stream) {
+  const int C = C1 + C2;
+  if (!x1 || !sums1 || !gamma || !beta || !y || C1 % 8 || C2 % 8 || C % groups || (C2 > 0 && (!x2 || !sums2))) return fail(CID_ERR_ARG, "cid_gn_apply_ch: bad arguments");
+  if (C > 4096 || groups > 256) return fail(CID_ERR_UNSUPPORTED, "cid_gn_apply_ch: C=%d > 4096 or groups=%d > 256", C, groups);
+  int slabs = grid_for((long long)HW * (C / 8), 256) / NB;
+  if (slabs < 1) slabs = 1;
+  launch_pdl(gn_apply_ch_kernel, dim3(slabs, NB), dim3(256), (4 * C + 2 * groups) * sizeof(float), static_cast<cudaStream_t>(stream),
+             (const uint16_t*)x1, C1, sums1, (const uint16_t*)x2, C2, sums2, HW, groups, (const uint16_t*)gamma, (const uint16_t*)beta, eps, silu,
+             (uint16_t*)y, int(dtype == CID_BF16));
+  CID_CHECK_LAUNCH("gn_apply_ch_kernel");
   return 0;
 }
 int cid_layernorm(const void* x, const void* gamma, const void* beta, void* y, long long rows, int C, float eps, int dtype, void* stream) {

@@ -127,6 +127,64 @@ gn_apply_kernel(const uint16_t* __restrict__ x1, int C1, const uint16_t* __restr
   }
 }
 
+// Same apply, statistics given PER CHANNEL by the producers' epilogues (gemm_tc2.cuh "fused GroupNorm statistics"): sums1[n, c, {sum, sumsq}]
+// for the C1 channels of x1, sums2 likewise for x2 (virtual concat: the 32 groups do not align with the concat boundary).
+// Each block folds the channel sums of its sample into group statistics (smem), then streams like gn_apply_kernel.
+__global__ void __launch_bounds__(256)
+gn_apply_ch_kernel(const uint16_t* __restrict__ x1, int C1, const float* __restrict__ sums1, const uint16_t* __restrict__ x2, int C2,
+                   const float* __restrict__ sums2, int HW, int groups, const uint16_t* __restrict__ gamma, const uint16_t* __restrict__ beta,
+                   float eps, int do_silu, uint16_t* __restrict__ y, int bf) {
+  griddep_wait();
+  extern __shared__ float aff[];                 // [2 * C] affine | [2 * C] channel sums | [2 * groups] group mean / rstd
+  const int C = C1 + C2, V = C / 8, cpg = C / groups;
+  float* chs = aff + 2 * C;
+  float* grp = aff + 4 * C;
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* src = (c < C1) ? sums1 + ((size_t)n * C1 + c) * 2 : sums2 + ((size_t)n * C2 + (c - C1)) * 2;
+    chs[2 * c] = src[0]; chs[2 * c + 1] = src[1];
+  }
+  __syncthreads();
+  const float inv_n = 1.f / (float(HW) * float(cpg));
+  for (int gi = threadIdx.x; gi < groups; gi += blockDim.x) {
+    float sm = 0.f, sq = 0.f;
+    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) { sm += chs[2 * c]; sq += chs[2 * c + 1]; }
+    const float mean = sm * inv_n;
+    grp[2 * gi] = mean;
+    grp[2 * gi + 1] = rsqrtf(fmaxf(sq * inv_n - mean * mean, 0.f) + eps);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int gi = c / cpg;
+    const float sc = grp[2 * gi + 1] * load16(gamma, c, bf);
+    aff[c] = sc;
+    aff[C + c] = load16(beta, c, bf) - grp[2 * gi] * sc;
+  }
+  __syncthreads();
+  const long long per_sample = (long long)HW * V;
+  const uint16_t* x1n = x1 + (size_t)n * HW * C1;
+  const uint16_t* x2n = x2 ? x2 + (size_t)n * HW * C2 : nullptr;
+  uint16_t* yn = y + (size_t)n * HW * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample; i += (long long)gridDim.x * blockDim.x) {
+    const int vec = int(i % V);
+    const long long pix = i / V;
+    const int c0 = vec * 8;
+    const uint4 u = (c0 < C1) ? *reinterpret_cast<const uint4*>(x1n + pix * C1 + c0)
+                              : *reinterpret_cast<const uint4*>(x2n + pix * C2 + (c0 - C1));
+    float f[8]; unpack8(u, f, bf);
+    const float4 s0 = *reinterpret_cast<const float4*>(aff + c0), s1 = *reinterpret_cast<const float4*>(aff + c0 + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(aff + C + c0), h1 = *reinterpret_cast<const float4*>(aff + C + c0 + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float v = fmaf(f[k], sc[k], sh[k]);
+      f[k] = do_silu ? silu_f(v) : v;
+    }
+    *reinterpret_cast<uint4*>(yn + pix * C + c0) = pack8(f, bf);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm
 // one warp per row, C <= 2048, C % 8 == 0; MAXV = ceil(C / 256) vectors per lane (templated: registers -> occupancy,
 // the kernel is a latency-bound streaming pass)

@@ -38,6 +38,11 @@ struct GemmArgs {
   void* Vt;                    // EPI_QKV: V^T [B*heads, hdim, ntok]
   int n_split, heads, hdim, ntok;
   float out_scale;
+  // GroupNorm statistics of the OUTPUT, fused into the epilogue (EPI_STORE only): per (sample, channel) sum and sum of squares of the stored
+  // values are accumulated into chan_stats[(row / stats_rows) * N + col][2] (fp32, zeroed by the caller).  Every 128-row tile must lie inside
+  // one sample (checked on the host).  NULL: off.
+  float* chan_stats;
+  int stats_rows;
 };
 
 constexpr int GEMM_BM = 128;

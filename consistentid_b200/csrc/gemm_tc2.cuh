@@ -33,7 +33,8 @@ struct Gemm2Smem {
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int BIAS_OFF = BAR_OFF + 256;             // 2 x BN floats
   static constexpr int FLAG_OFF = BIAS_OFF + 2 * BN * 4;     // split-K "last arriver" flag
-  static constexpr int TOTAL = FLAG_OFF + 16 + 1024;
+  static constexpr int STAT_OFF = FLAG_OFF + 16;             // 2 x [sum | sumsq] x BN floats: per-tile column statistics (fused GroupNorm stats)
+  static constexpr int TOTAL = STAT_OFF + 2 * 2 * BN * 4 + 1024;
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -47,6 +48,42 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_st16_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Column sums over the 32 rows held by the lanes of a warp: in v[16] (one row per lane), out: the sum of column
+// col_of_lane(lane) in every lane (lanes 2k and 2k+1 hold the same column).  16 shuffles instead of 16 x 5.
+__device__ __forceinline__ int colsum_col_of_lane(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+__device__ __forceinline__ float warp_colsum16(float (&s)[16], int lane) {
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = hi ? s[i] : s[i + 8], keep = hi ? s[i + 8] : s[i];
+      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = hi ? s[i] : s[i + 4], keep = hi ? s[i + 4] : s[i];
+      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = hi ? s[i] : s[i + 2], keep = hi ? s[i + 2] : s[i];
+      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool hi = lane & 2;
+    const float send = hi ? s[0] : s[1], keep = hi ? s[1] : s[0];
+    s[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return s[0] + __shfl_xor_sync(0xffffffffu, s[0], 1);
+}
+
 // Work list of one CTA: `full_iters` whole tiles (tile = blockIdx.x + i*gridDim.x), then at most one tail item: a whole tail tile
 // (ksplit <= 1, blockIdx.x < tail_tiles) or K-range `split` of tail tile blockIdx.x / ksplit.
 struct GemmSched {
@@ -56,7 +93,10 @@ struct GemmSched {
 };
 struct GemmWork { int tile, kb0, kb1, split, tail_idx; };
 
-template <int BN, int STAGES>
+// EPI (epilogue flavour: EPI_STORE covers the plain / GELU / fused-statistics stores, EPI_GEGLU, EPI_QKV) and BF (0 fp16, 1 bf16) are
+// compile-time: the generic kernel was 41 k SASS instructions at BN = 256 (every flavour x both 16-bit types, fully unrolled) and ncu showed
+// instruction-fetch stalls (`no_instruction` 2.0-3.5 per issue) on the epilogue-bound GEMMs; a specialised instance holds only its own path.
+template <int BN, int STAGES, int EPI, int BF>
 __global__ void __launch_bounds__(GEMM2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmB, const GemmArgs g, const int n_tiles, const GemmSched sched) {
@@ -73,6 +113,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
   auto acc_empty = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + SM::BAR_OFF + 8 * (2 * STAGES + 4));
   float* bias_s = reinterpret_cast<float*>(smem_gen + SM::BIAS_OFF);
+  float* stat_s = reinterpret_cast<float*>(smem_gen + SM::STAT_OFF);
 
   const int warp = warp_id();
   const int lane = lane_id();
@@ -153,7 +194,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    const uint32_t idesc = make_idesc(GEMM_BM, BN, g.is_bf16);
+    const uint32_t idesc = make_idesc(GEMM_BM, BN, BF);
     int stage = 0; uint32_t phase = 0;
     const uint32_t a_lo0 = desc_lo(smem_base);
     for (int it = 0; it < n_work; ++it) {
@@ -181,15 +222,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     }
   } else {
     // ================================================================ epilogue (warps 2..9)
-    // (generic lambda: the 16-bit flavour becomes a compile-time constant, so pack/unpack fold to one conversion)
-    auto epilogue = [&](auto bf_tag) {
-    constexpr int bf = decltype(bf_tag)::value;
+    constexpr int bf = BF;
     const int ew = warp - 2;
     const int quarter = warp & 3;
     const int half = ew >> 2;                              // which half of the tile's columns this warp drains
     const int r = quarter * 32 + lane;
     const int et = threadIdx.x - 64;                       // 0..255
-    const bool geglu = g.epi == EPI_GEGLU;
+    constexpr bool geglu = EPI == EPI_GEGLU;
     // column range [c_beg, c_end) in 16-column chunks (GEGLU: over the value half only)
     constexpr int NCHUNK = BN / 16;
     constexpr int NCHUNK_G = (BN / 2) / 16 > 0 ? (BN / 2) / 16 : 1;
@@ -210,6 +249,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
       grow_ = ((long long)n * g.H + y) * g.W + x;
       return (dn < g.TN) && (n < g.NB) && (y < g.H) && (x < g.W);
     };
+    // global row of accumulator row 0 of tile `tile_` (the statistics' sample index: all rows of a tile share it, host-checked)
+    auto my_row_base = [&](int tile_) -> long long {
+      const int mt_ = tile_ / n_tiles;
+      if (g.a_mode == A_GEMM) return (long long)mt_ * GEMM_BM;
+      int tn0, ty0, tx0;
+      tile_origin(mt_, tn0, ty0, tx0);
+      return ((long long)tn0 * g.H + ty0) * g.W + tx0;
+    };
     volatile int* last_flag = reinterpret_cast<volatile int*>(smem_gen + SM::FLAG_OFF);
     for (int it = 0; it < n_work; ++it) {
       const GemmWork w = get_work(it);
@@ -224,6 +271,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
       // stage this tile's bias slice (fp32) in smem; buffer alternates with the accumulator
       float* bs = bias_s + ab * BN;
       for (int j = et; j < BN; j += GEMM2_EPI_THREADS) bs[j] = (g.bias && n0 + j < g.N) ? load16(g.bias, n0 + j, bf) : 0.f;
+      const bool do_stats = EPI == EPI_STORE && g.chan_stats != nullptr;
+      float* st = stat_s + ab * 2 * BN;
+      if (do_stats) for (int j = et; j < 2 * BN; j += GEMM2_EPI_THREADS) st[j] = 0.f;
       // prefetch residual rows for this thread's chunks (latency overlaps the wait for the accumulator; prefetching a whole
       // tile ahead was measured: no gain at BN=160, register spills at BN=256)
       uint4 res[MAXCH][2];
@@ -339,7 +389,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         // (measured: +5 % on the bias/residual epilogues, -7 % on the scattered transposed-V stores of the QKV epilogue, which keeps the
         // plain load -> wait -> store order)
         uint32_t acc2[2][16];
-        const bool pipelined = g.epi != EPI_QKV;
+        constexpr bool pipelined = EPI != EPI_QKV;
         if (pipelined && ch_beg < ch_end) tmem_ld_x16(t_row + ch_beg * 16, acc2[0]);
 #pragma unroll
         for (int c = 0; c < MAXCH; ++c) {
@@ -350,9 +400,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             if (pipelined && ch + 1 < ch_end) tmem_ld_x16(t_row + (ch + 1) * 16, acc2[(c + 1) & 1]);
             const uint32_t (&a)[16] = acc2[c & 1];
             const int col0 = n0 + ch * 16;
-            if (row_ok && col0 < g.N) {
-              const bool full = (col0 + 16 <= g.N);
-              float v[16];
+            const bool full = (col0 + 16 <= g.N);
+            const bool active = row_ok && col0 < g.N;
+            float v[16];
+            if (active) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(a[j]) + bs[ch * 16 + j];
               if (g.rowbias) {
@@ -367,7 +418,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                   for (int j = 0; j < 16; ++j) if (full || col0 + j < g.N) v[j] += load16(rb, j, bf);
                 }
               }
-              if (g.epi == EPI_QKV && col0 >= g.n_split) {
+              if (EPI == EPI_QKV && col0 >= g.n_split) {
                 const int b = int(grow / g.ntok), tok = int(grow - (long long)b * g.ntok);
           const size_t vC = (size_t)g.heads * g.hdim;
 #pragma unroll
@@ -393,7 +444,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] *= g.out_scale;
                 }
-                if (g.epi == EPI_GELU) {
+                if (EPI == EPI_STORE && g.epi == EPI_GELU) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
                 }
@@ -410,14 +461,33 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 }
               }
             }
+            if (do_stats && col0 < g.N) {                   // warp-uniform: every lane joins the shuffles, inactive rows / columns add 0
+              float s1[16], s2[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float x = (active && (full || col0 + j < g.N)) ? v[j] : 0.f;
+                s1[j] = x; s2[j] = x * x;
+              }
+              const float cs = warp_colsum16(s1, lane), cq = warp_colsum16(s2, lane);
+              if ((lane & 1) == 0) {
+                const int cc = ch * 16 + colsum_col_of_lane(lane);
+                atomicAdd(&st[cc], cs); atomicAdd(&st[BN + cc], cq);
+              }
+            }
           }
+        }
+        if (do_stats) {
+          // the four row quarters of this tile were combined in smem: one global reduction per column and statistic
+          epi_bar_sync();
+          const long long srow = my_row_base(tile);
+          float* dst = g.chan_stats + ((srow / g.stats_rows) * g.N + n0) * 2;
+          for (int j = et; j < BN; j += GEMM2_EPI_THREADS)
+            if (n0 + j < g.N) { atomicAdd(dst + 2 * j, st[j]); atomicAdd(dst + 2 * j + 1, st[BN + j]); }
         }
       }
       tc_fence_before();
       mbar_arrive(acc_empty(ab));                           // this thread no longer reads accumulator `ab`
     }
-    };
-    if (g.is_bf16) epilogue(std::integral_constant<int, 1>{}); else epilogue(std::integral_constant<int, 0>{});
   }
 
   __syncthreads();

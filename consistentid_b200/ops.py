@@ -82,9 +82,10 @@ def _chk(t, name):
 
 
 def gemm(a, w, out, bias=None, residual=None, rowbias=None, rows_per_group=1, a2=None, epi=EPI_STORE, vt=None,
-         n_split=0, heads=0, hdim=0, ntok=0, out_scale=1.0):
+         n_split=0, heads=0, hdim=0, ntok=0, out_scale=1.0, chan_stats=None, stats_rows=0):
     """out[M, :] = epi([a | a2] @ w.T + bias + rowbias[row // rows_per_group] + residual) * out_scale.
-    a: [M, K1] (last-dim contiguous, row pitch a.stride(0)); w: [N, K1+K2] contiguous."""
+    a: [M, K1] (last-dim contiguous, row pitch a.stride(0)); w: [N, K1+K2] contiguous.
+    chan_stats: fp32 [M / stats_rows, N, 2] (zeroed by the caller) += per (sample, column) sum / sum of squares of ``out``."""
     _chk(a, "a")
     M, K1 = a.shape
     K2 = 0 if a2 is None else a2.shape[1]
@@ -99,11 +100,11 @@ def gemm(a, w, out, bias=None, residual=None, rowbias=None, rows_per_group=1, a2
         call("cid_gemm", _p(a), a.stride(0), _p(a2), 0 if a2 is None else a2.stride(0), K1, K2, _p(w), _p(out), out.stride(0),
              M, N, _p(bias), _p(residual), 0 if residual is None else residual.stride(0), _p(rowbias), rows_per_group,
              0 if rowbias is None else rowbias.stride(0), epi, _p(vt), n_split, heads, hdim, ntok, float(out_scale), _dt(a),
-             ws.data_ptr(), WORKSPACE_BYTES, _stream())
+             ws.data_ptr(), WORKSPACE_BYTES, _p(chan_stats), stats_rows, _stream())
     return out
 
 
-def conv3x3(x, w, out, NB, H, W, Cin, Cout, bias=None, residual=None, rowbias=None, stride2=False, out_scale=1.0):
+def conv3x3(x, w, out, NB, H, W, Cin, Cout, bias=None, residual=None, rowbias=None, stride2=False, out_scale=1.0, chan_stats=None):
     """x: NHWC [NB,H,W,Cin] (or phase-split [NB,4,H,W,Cin] when stride2; H,W = output dims); w: [Cout, 9*Cin];
     out: [NB*H*W, >=Cout] rows."""
     M = NB * H * W
@@ -111,7 +112,7 @@ def conv3x3(x, w, out, NB, H, W, Cin, Cout, bias=None, residual=None, rowbias=No
     with _prof("conv3x3", 2.0 * M * Cout * 9 * Cin, 2.0 * (M * Cin * (4 if stride2 else 1) + 9 * Cin * Cout + M * Cout), (M, Cout, 9 * Cin, 0)):
         call("cid_conv3x3", _p(x), _p(w), _p(out), out.stride(0), NB, H, W, Cin, Cout, 1 if stride2 else 0, _p(bias), _p(residual),
              0 if residual is None else residual.stride(0), _p(rowbias), 0 if rowbias is None else rowbias.stride(0),
-             float(out_scale), _dt(x), ws.data_ptr(), WORKSPACE_BYTES, _stream())
+             float(out_scale), _dt(x), ws.data_ptr(), WORKSPACE_BYTES, _p(chan_stats), _stream())
     return out
 
 
@@ -146,6 +147,14 @@ def gn_apply(x1, C1, x2, C2, NB, HW, groups, sums, gamma, beta, eps, silu, out, 
     with _prof("gn_apply", 0.0, 4.0 * NB * HW * (C1 + C2), (NB * HW, C1 + C2)):                     # one read + one write
         call("cid_gn_apply", _p(x1), C1, _p(x2), C2, NB, HW, groups, _p(sums), _p(gamma), _p(beta), float(eps), 1 if silu else 0,
              _p(out), _p(zero_next), _dt(x1), _stream())
+    return out
+
+
+def gn_apply_ch(x1, C1, sums1, x2, C2, sums2, NB, HW, groups, gamma, beta, eps, silu, out):
+    """GroupNorm apply with per-(sample, channel) statistics from the producers' epilogues (``chan_stats`` of gemm / conv3x3)."""
+    with _prof("gn_apply", 0.0, 4.0 * NB * HW * (C1 + C2), (NB * HW, C1 + C2)):
+        call("cid_gn_apply_ch", _p(x1), C1, _p(sums1), _p(x2), C2, _p(sums2), NB, HW, groups, _p(gamma), _p(beta), float(eps), 1 if silu else 0,
+             _p(out), _dt(x1), _stream())
     return out
 
 

@@ -310,8 +310,36 @@ class B200UNet:
         ops.skinny_linear(emb, P["temb_all.w"], P["temb_all.b"], temb_all, NB, P.temb_total, T, silu_in=True)
         return emb, temb_all
 
+    # ---- GroupNorm statistics fused into the producers' epilogues -------------------------------------------------------------
+    STATS_ARENA_FLOATS = 4 << 20        # 16 MB: >= 2 * NB * sum(C) over every normalised tensor of a forward at the BASELINE batches
+
+    def _stats_begin(self):
+        """Start of a forward: one memset zeroes the per-(sample, channel) statistics slots the producers of this forward will fill."""
+        arena = self._buf("gn_chan_stats", (self.STATS_ARENA_FLOATS,), torch.float32)
+        used = getattr(self, "_stats_used", None)
+        (arena if used is None else arena[:used]).zero_()
+        self._stats_off, self._stats = 0, {}
+
+    def _stats_slot(self, out, HW, C):
+        """Statistics slot for tensor ``out`` [NB*HW, C] about to be produced by a conv / GEMM, or None when the fused path does not apply
+        (a 128-row tile would span two samples: HW % 128 != 0 - the 8x8 level; those tensors take the standalone statistics kernel)."""
+        NB = self._plan[0]
+        n = NB * C * 2
+        if HW % 128 != 0 or self._stats_off + n > self.STATS_ARENA_FLOATS:
+            self._stats.pop(out.data_ptr(), None)
+            return None
+        v = self._buf("gn_chan_stats", (self.STATS_ARENA_FLOATS,), torch.float32)[self._stats_off:self._stats_off + n]
+        self._stats_off += (n + 63) // 64 * 64
+        self._stats[out.data_ptr()] = v
+        return v
+
     def _groupnorm(self, x1, C1, x2, C2, HW, g, b, eps, silu, out):
         NB, G = self._plan[0], self.spec.norm_num_groups
+        s1 = self._stats.get(x1.data_ptr())
+        s2 = self._stats.get(x2.data_ptr()) if x2 is not None else None
+        if s1 is not None and (x2 is None or s2 is not None):
+            ops.gn_apply_ch(x1, C1, s1, x2, C2, s2, NB, HW, G, g, b, eps, silu, out)
+            return
         # two alternating statistics buffers: the first GroupNorm of a forward zeroes its own (one memset), every apply zeroes the
         # buffer the next GroupNorm will accumulate into
         k = self._gn_k
@@ -331,7 +359,8 @@ class B200UNet:
         self._groupnorm(x, c_x, skip, r.skip_ch, HW, P[r.name + ".n1.g"], P[r.name + ".n1.b"], spec.norm_eps, True, act)
         h1 = buf("res_h1", (M, r.cout))
         o = P.temb_off[r.name]
-        ops.conv3x3(act, P[r.name + ".c1.w"], h1, NB, h, w, r.cin, r.cout, bias=P[r.name + ".c1.b"], rowbias=temb_all[:, o:o + r.cout])
+        ops.conv3x3(act, P[r.name + ".c1.w"], h1, NB, h, w, r.cin, r.cout, bias=P[r.name + ".c1.b"], rowbias=temb_all[:, o:o + r.cout],
+                    chan_stats=self._stats_slot(h1, HW, r.cout))
         act2 = buf("act", (M, r.cout))
         self._groupnorm(h1, r.cout, None, 0, HW, P[r.name + ".n2.g"], P[r.name + ".n2.b"], spec.norm_eps, True, act2)
         if r.cin != r.cout:
@@ -340,7 +369,8 @@ class B200UNet:
         else:
             res = x
         out = buf(out_name, (M, r.cout))
-        ops.conv3x3(act2, P[r.name + ".c2.w"], out, NB, h, w, r.cout, r.cout, bias=P[r.name + ".c2.b"], residual=res)
+        ops.conv3x3(act2, P[r.name + ".c2.w"], out, NB, h, w, r.cout, r.cout, bias=P[r.name + ".c2.b"], residual=res,
+                    chan_stats=self._stats_slot(out, HW, r.cout))
         return out
 
     def _transformer(self, tf, x, h, w, out_name, kv):
@@ -373,7 +403,8 @@ class B200UNet:
             ops.gemm(ln, P[b + ".ff1.w"], ffm, bias=P[b + ".ff1.b"], epi=EPI_GEGLU)
             ops.gemm(ffm, P[b + ".ff2.w"], t, bias=P[b + ".ff2.b"], residual=t)
         out = buf(out_name, (M, C))
-        ops.gemm(t, P[tf.name + ".po.w"], out, bias=P[tf.name + ".po.b"], residual=x)
+        st = self._stats_slot(out, HW, C)
+        ops.gemm(t, P[tf.name + ".po.w"], out, bias=P[tf.name + ".po.b"], residual=x, chan_stats=st, stats_rows=HW if st is not None else 0)
         return out
 
     def _downsample(self, x, i, h, w, c):
@@ -382,7 +413,8 @@ class B200UNet:
         ops.phase_split(x, ps, NB, h, w, c)
         nm = f"down_blocks.{i}.downsamplers.0.conv"
         out = buf(f"h.{nm}", (NB * (h // 2) * (w // 2), c))
-        ops.conv3x3(ps, P[nm + ".w"], out, NB, h // 2, w // 2, c, c, bias=P[nm + ".b"], stride2=True)
+        ops.conv3x3(ps, P[nm + ".w"], out, NB, h // 2, w // 2, c, c, bias=P[nm + ".b"], stride2=True,
+                    chan_stats=self._stats_slot(out, (h // 2) * (w // 2), c))
         return out
 
     def _add_residual(self, dst, res, c):
@@ -407,13 +439,15 @@ class B200UNet:
         spec, P, buf = self.spec, self.params, self._buf
         kv = self._kv[key]
         self._gn_k = 0
+        self._stats_begin()
         down_res, mid_res = residuals
         emb, temb_all = self._time_embedding(key)
         # --- stem
         h, w = H, W
         c0 = spec.block_out_channels[0]
         x = buf("h.conv_in", (NB * h * w, c0))
-        ops.conv3x3(buf("x_in", (NB * H * W, CIN_PAD)), P["conv_in.w"], x, NB, h, w, CIN_PAD, c0, bias=P["conv_in.b"])
+        ops.conv3x3(buf("x_in", (NB * H * W, CIN_PAD)), P["conv_in.w"], x, NB, h, w, CIN_PAD, c0, bias=P["conv_in.b"],
+                    chan_stats=self._stats_slot(x, h * w, c0))
         skips = [(x, c0)]
         for kind, i, layers, has_sampler in walk(spec):
             if kind == "mid" and down_res is not None:
@@ -450,13 +484,14 @@ class B200UNet:
                     h, w = 2 * h, 2 * w
                     nm = f"up_blocks.{i}.upsamplers.0.conv"
                     x2 = buf(f"h.{nm}", (NB * h * w, c))
-                    ops.conv3x3(up, P[nm + ".w"], x2, NB, h, w, c, c, bias=P[nm + ".b"])
+                    ops.conv3x3(up, P[nm + ".w"], x2, NB, h, w, c, c, bias=P[nm + ".b"], chan_stats=self._stats_slot(x2, h * w, c))
                     x = x2
         # --- head
         act = buf("act", (NB * h * w, c0))
         self._groupnorm(x, c0, None, 0, h * w, P["norm_out.g"], P["norm_out.b"], spec.norm_eps, True, act)
         eps = buf("eps", (NB * H * W, 4))
         ops.conv3x3(act, P["conv_out.w"], eps, NB, h, w, c0, spec.out_channels, bias=P["conv_out.b"])
+        self._stats_used = self._stats_off
         return eps
 
     def _to_rows(self, nchw, c):

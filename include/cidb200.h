@@ -44,18 +44,24 @@ int cid_gemm_tile_n(int N, int epi);
  * GEGLU / FF linears, Transformer2D proj_in/out, ResnetBlock2D 1x1 conv_shortcut (diffusers 0.23).
  *   epi = GEGLU : B rows interleaved per tile (value half | gate half); writes C[M, N/2] = v * gelu(g).
  *   epi = QKV   : columns >= n_split are V and are written TRANSPOSED to Vt[(row/ntok)*heads + h, dd, row%ntok].
- *   epi = GELU  : C = gelu_erf(acc + bias (+ residual)) - the fc1 + activation of the CLIP vision MLP. */
+ *   epi = GELU  : C = gelu_erf(acc + bias (+ residual)) - the fc1 + activation of the CLIP vision MLP.
+ *   chan_stats  : non-NULL (plain store epilogue only) = GroupNorm statistics of the OUTPUT fused into the epilogue: per (sample, column)
+ *                 sum and sum of squares are ADDED to chan_stats[(row / stats_rows) * N + col][2] (fp32, zeroed by the caller); stats_rows =
+ *                 rows per sample, a multiple of 128.  Consumed by cid_gn_apply_ch: the standalone statistics pass (one re-read of the
+ *                 tensor per GroupNorm) disappears. */
 int cid_gemm(const void* A, long long lda, const void* A2, long long lda2, int K1, int K2, const void* B,
              void* C, long long ldc, int M, int N, const void* bias, const void* residual, long long ldr,
              const void* rowbias, int rows_per_group, long long ld_rowbias, int epi, void* Vt, int n_split, int heads,
-             int hdim, int ntok, float out_scale, int dtype, void* workspace, unsigned long long ws_bytes, void* stream);
+             int hdim, int ntok, float out_scale, int dtype, void* workspace, unsigned long long ws_bytes, float* chan_stats,
+             int stats_rows, void* stream);
 
 /* 3x3 convolution, padding 1, as implicit GEMM over NHWC.  X: [NB,H,W,Cin] (stride 1) or the phase-split copy
  * [NB,4,H,W,Cin] of a [NB,2H,2W,Cin] tensor (stride2 = 1; H,W are OUTPUT dims).  Wt: [Cout, 9*Cin] = (ky,kx,c) order.
- * Y[NB*H*W, ldy].  Replaces ResnetBlock2D.conv1/conv2, Downsample2D.conv, Upsample2D.conv, conv_in, conv_out. */
+ * Y[NB*H*W, ldy].  Replaces ResnetBlock2D.conv1/conv2, Downsample2D.conv, Upsample2D.conv, conv_in, conv_out.
+ * chan_stats as in cid_gemm (rows per sample = H*W; needs H*W >= 128 so that no 128-pixel tile spans two samples). */
 int cid_conv3x3(const void* X, const void* Wt, void* Y, long long ldy, int NB, int H, int W, int Cin, int Cout,
                 int stride2, const void* bias, const void* residual, long long ldr, const void* rowbias,
-                long long ld_rowbias, float out_scale, int dtype, void* workspace, unsigned long long ws_bytes, void* stream);
+                long long ld_rowbias, float out_scale, int dtype, void* workspace, unsigned long long ws_bytes, float* chan_stats, void* stream);
 
 /* softmax(Q K^T / sqrt(d)) V per (sample, head).  Q,K: [B,N,H,d] views with row pitch q_pitch/k_pitch;
  * Vt: [B*H, d, N] (keys contiguous); O: [B,N,H*d] pitch ldo.  Replaces attention.py:152-159. */
@@ -78,6 +84,10 @@ int cid_gn_stats(const void* x1, int C1, const void* x2, int C2, int NB, int HW,
                  void* stream);
 int cid_gn_apply(const void* x1, int C1, const void* x2, int C2, int NB, int HW, int groups, const float* sums,
                  const void* gamma, const void* beta, float eps, int silu, void* y, float* zero_next, int dtype, void* stream);
+/* gn_apply with the statistics given per (sample, channel) by the producers' epilogues (cid_gemm / cid_conv3x3 chan_stats): sums1[NB, C1, 2] for
+ * x1, sums2[NB, C2, 2] for x2 (NULL when C2 == 0).  Group statistics are formed on the fly (the 32 groups do not align with the concat boundary). */
+int cid_gn_apply_ch(const void* x1, int C1, const float* sums1, const void* x2, int C2, const float* sums2, int NB, int HW, int groups,
+                    const void* gamma, const void* beta, float eps, int silu, void* y, int dtype, void* stream);
 int cid_layernorm(const void* x, const void* gamma, const void* beta, void* y, long long rows, int C, float eps, int dtype, void* stream);
 int cid_upsample2x(const void* x, void* y, int NB, int H, int W, int C, void* stream);
 int cid_phase_split(const void* x, void* y, int NB, int H, int W, int C, void* stream);

@@ -21,8 +21,15 @@ def _f(t):
     return None if t is None else t.float()
 
 
+def _add_chan_stats(chan_stats, y, rows_per_sample):
+    if chan_stats is not None:
+        M, N = y.shape
+        yy = y.float().view(M // rows_per_sample, rows_per_sample, N)
+        chan_stats.view(-1, N, 2).add_(torch.stack([yy.sum(1), (yy * yy).sum(1)], dim=-1))
+
+
 def gemm(a, w, out, bias=None, residual=None, rowbias=None, rows_per_group=1, a2=None, epi=0, vt=None, n_split=0, heads=0, hdim=0, ntok=0,
-         out_scale=1.0):
+         out_scale=1.0, chan_stats=None, stats_rows=0):
     x = a.float() if a2 is None else torch.cat([a.float(), a2.float()], dim=1)
     y = x @ w.float().T
     M, N = y.shape
@@ -46,10 +53,11 @@ def gemm(a, w, out, bias=None, residual=None, rowbias=None, rows_per_group=1, a2
     if epi == 3:          # EPI_GELU
         y = F.gelu(y)
     out.copy_(y)
+    _add_chan_stats(chan_stats, y, stats_rows)
     return out
 
 
-def conv3x3(x, w, out, NB, H, W, Cin, Cout, bias=None, residual=None, rowbias=None, stride2=False, out_scale=1.0):
+def conv3x3(x, w, out, NB, H, W, Cin, Cout, bias=None, residual=None, rowbias=None, stride2=False, out_scale=1.0, chan_stats=None):
     wt = w.float().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)                         # [Cout, 9*Cin] is (ky, kx, c) order
     if stride2:                                                                      # x: phase-split copy [NB, 4, H, W, Cin] of [NB, 2H, 2W, Cin]
         ps = x.float().view(NB, 2, 2, H, W, Cin)
@@ -68,6 +76,7 @@ def conv3x3(x, w, out, NB, H, W, Cin, Cout, bias=None, residual=None, rowbias=No
     if residual is not None:
         y = y + residual.float()[:, :Cout]
     out[:, :Cout] = y * out_scale
+    _add_chan_stats(chan_stats, y * out_scale, H * W)
     return out
 
 
@@ -130,6 +139,14 @@ def gn_apply(x1, C1, x2, C2, NB, HW, groups, sums, gamma, beta, eps, silu, out, 
     if zero_next is not None:
         zero_next.zero_()
     return out
+
+
+def gn_apply_ch(x1, C1, sums1, x2, C2, sums2, NB, HW, groups, gamma, beta, eps, silu, out):
+    ch = sums1.view(NB, C1, 2)
+    if C2:
+        ch = torch.cat([ch, sums2.view(NB, C2, 2)], dim=1)
+    sums = ch.view(NB, groups, (C1 + C2) // groups, 2).sum(2)
+    return gn_apply(x1, C1, x2, C2, NB, HW, groups, sums, gamma, beta, eps, silu, out)
 
 
 def layernorm(x, gamma, beta, out, rows, C, eps=1e-5):
@@ -254,7 +271,7 @@ def ensure_workspace(device=None):
     return None
 
 
-_NAMES = ("gemm conv3x3 attn_self pack_cross_kv attn_cross gn_stats gn_apply layernorm layernorm_rows upsample2x phase_split nchw_to_nhwc_pad "
+_NAMES = ("gemm conv3x3 attn_self pack_cross_kv attn_cross gn_stats gn_apply gn_apply_ch layernorm layernorm_rows upsample2x phase_split nchw_to_nhwc_pad "
           "rows_to_nchw add_inplace silu_inplace timestep_embed skinny_linear softmax_rows perceiver_attn cfg_sched_step latents_to_input "
           "advance_step inpaint_blend ensure_workspace").split()
 

@@ -184,6 +184,52 @@ def check_gemm_gelu(M=300, N=1280, K=320, dtype=torch.float16, seed=0):
     return _report(f"gemm_gelu {M}x{N}x{K}", out, ref, 8e-3)
 
 
+def check_conv_stats(NB=2, H=16, W=16, Cin=128, Cout=320, dtype=torch.float16, seed=0, residual=True):
+    """Fused GroupNorm statistics of the conv epilogue + cid_gn_apply_ch vs torch group_norm of the stored output."""
+    ops = _ops()
+    x = _rand((NB * H * W, Cin), dtype, seed)
+    w = _rand((Cout, 9 * Cin), dtype, seed + 1, (9 * Cin) ** -0.5)
+    b = _rand((Cout,), dtype, seed + 2)
+    res = _rand((NB * H * W, Cout), dtype, seed + 3) if residual else None
+    out = torch.empty((NB * H * W, Cout), dtype=dtype, device=DEV)
+    stats = torch.zeros((NB, Cout, 2), dtype=torch.float32, device=DEV)
+    ops.conv3x3(x, w, out, NB, H, W, Cin, Cout, bias=b, residual=res, chan_stats=stats)
+    torch.cuda.synchronize()
+    o = out.float().view(NB, H * W, Cout)
+    want = torch.stack([o.sum(1), (o * o).sum(1)], dim=-1)
+    r1 = _report(f"conv_stats sums {NB}x{H}x{W} {Cin}->{Cout}", stats.view(NB * Cout, 2), want.view(NB * Cout, 2), 2e-3)
+    g, be = _rand((Cout,), dtype, seed + 4), _rand((Cout,), dtype, seed + 5)
+    y = torch.empty_like(out)
+    ops.gn_apply_ch(out, Cout, stats, None, 0, None, NB, H * W, 32, g, be, 1e-5, True, y)
+    torch.cuda.synchronize()
+    ref = F.silu(F.group_norm(o.transpose(1, 2), 32, g.float(), be.float(), 1e-5)).transpose(1, 2).reshape(NB * H * W, Cout)
+    r2 = _report("gn_apply_ch", y, ref, 8e-3)
+    r1["ok"] = r1["ok"] and r2["ok"]; r1["apply_max_err"] = r2["max_err"]
+    return r1
+
+
+def check_gemm_stats_concat(NB=2, HW=256, C1=640, C2=320, K=320, dtype=torch.bfloat16, seed=0):
+    """Two producers (GEMM with residual, conv) feed one GroupNorm over their virtual concat: 960 channels / 32 groups = 30 per group, the
+    group boundaries do not align with the concat boundary."""
+    ops = _ops()
+    M = NB * HW
+    a, w, b = _rand((M, K), dtype, seed), _rand((C1, K), dtype, seed + 1, K ** -0.5), _rand((C1,), dtype, seed + 2)
+    res = _rand((M, C1), dtype, seed + 3)
+    o1 = torch.empty((M, C1), dtype=dtype, device=DEV); s1 = torch.zeros((NB, C1, 2), dtype=torch.float32, device=DEV)
+    ops.gemm(a, w, o1, bias=b, residual=res, chan_stats=s1, stats_rows=HW)
+    h = int(HW ** 0.5)
+    x2, w2 = _rand((M, 64), dtype, seed + 4), _rand((C2, 9 * 64), dtype, seed + 5, (9 * 64) ** -0.5)
+    o2 = torch.empty((M, C2), dtype=dtype, device=DEV); s2 = torch.zeros((NB, C2, 2), dtype=torch.float32, device=DEV)
+    ops.conv3x3(x2, w2, o2, NB, h, h, 64, C2, chan_stats=s2)
+    g, be = _rand((C1 + C2,), dtype, seed + 6), _rand((C1 + C2,), dtype, seed + 7)
+    y = torch.empty((M, C1 + C2), dtype=dtype, device=DEV)
+    ops.gn_apply_ch(o1, C1, s1, o2, C2, s2, NB, HW, 32, g, be, 1e-6, False, y)
+    torch.cuda.synchronize()
+    cat = torch.cat([o1.float().view(NB, HW, C1), o2.float().view(NB, HW, C2)], dim=-1)
+    ref = F.group_norm(cat.transpose(1, 2), 32, g.float(), be.float(), 1e-6).transpose(1, 2).reshape(M, C1 + C2)
+    return _report(f"gemm+conv stats -> gn_apply_ch concat {C1}+{C2}", y, ref, 1.6e-2)
+
+
 def check_attn_cross(B=2, H=2, N=256, d=64, dtype=torch.float16, n_text=77, n_ip=4, ip_scale=1.0, seed=0):
     ops = _ops()
     C = H * d
@@ -457,6 +503,11 @@ CHECKS = {
     "attn_cross_d80": (check_attn_cross, dict(B=1, H=4, N=200, d=80)),
     "attn_cross_d160": (check_attn_cross, dict(B=2, H=2, N=64, d=160, dtype=B16)),
     "attn_cross_d32": (check_attn_cross, dict(B=2, H=2, N=128, d=32)),
+    "conv_stats": (check_conv_stats, dict(NB=2, H=16, W=16, Cin=128, Cout=320)),
+    "conv_stats_1280": (check_conv_stats, dict(NB=3, H=16, W=16, Cin=64, Cout=1280, dtype=B16, residual=False)),
+    "conv_stats_w128": (check_conv_stats, dict(NB=1, H=4, W=128, Cin=64, Cout=160)),
+    "conv_stats_split": (check_conv_stats, dict(NB=16, H=16, W=16, Cin=640, Cout=1280)),
+    "gemm_stats_concat": (check_gemm_stats_concat, {}),
     "gn_320": (check_groupnorm, dict(C1=320)),
     "gn_concat": (check_groupnorm, dict(C1=640, C2=320, HW=1024)),
     "gn_2560": (check_groupnorm, dict(C1=1280, C2=1280, HW=64, NB=3, dtype=B16)),

@@ -149,3 +149,29 @@ def test_unet_forward_with_aggressive_tail_split():
     torch.cuda.synchronize()
     assert torch.isfinite(split).all()
     assert (split - base).abs().max().item() <= 2e-2 * base.abs().max().item()
+
+
+@pytest.mark.gpu
+def test_prompt_cache_with_recycled_prompt_allocations():
+    """a reference-style loop builds its prompt with a fresh torch.cat every step; the caching allocator hands the freed block
+    to the NEXT step's (different) prompt at the same address.  The drop-in ``unet(...)`` path must never serve the previous prompt's K/V."""
+    dtype = torch.float16
+    cfg = tiny_config("sd15")
+    ref = synth.build_ref_unet(cfg, rank=16)
+    B, h = 1, cfg.sample_size
+    null, aug, txt = (t.cuda().to(dtype) for t in synth.synth_prompts(cfg.cross_attention_dim))
+    x = synth.synth_latents(2 * B, h, h, seed=3).cuda().to(dtype)
+    t = torch.tensor(601)
+    eng = _engine_from_oracle(ref, dtype, 16)
+    keep_txt, keep_aug = torch.cat([null, txt]), torch.cat([null, aug])
+    want = {0: eng(x, t, keep_txt, cross_attention_kwargs={}).sample.float().clone(), 1: eng(x, t, keep_aug, cross_attention_kwargs={}).sample.float().clone()}
+    assert (want[0] - want[1]).abs().max().item() > 1e-2            # the two prompts really give different outputs
+    ptrs = set()
+    for step in range(8):
+        ehs = torch.cat([null, txt if step % 2 == 0 else aug])       # fresh tensor, previous one freed below -> address reuse
+        ptrs.add(ehs.data_ptr())
+        got = eng(x, t, ehs, cross_attention_kwargs={}).sample.float()
+        err = (got - want[step % 2]).abs().max().item()
+        assert err <= 2e-2 * want[step % 2].abs().max().item(), (step, err)
+        del ehs, got
+    print(f"[prompt cache] distinct prompt addresses over 8 steps: {len(ptrs)}")
