@@ -12,10 +12,12 @@
 
 #include "../../include/cidb200.h"
 #include "attn_cross.cuh"
-#ifdef CID_ATTN_V3
+#if defined(CID_ATTN_V3)
 #include "attn_tc3.cuh"          // A/B builds only (tools/build_variant.sh): the round-1 kernel
+#elif defined(CID_ATTN_V4)
+#include "attn_tc4.cuh"          // A/B builds only: chunk-pipelined softmax, single P buffer
 #else
-#include "attn_tc4.cuh"
+#include "attn_tc5.cuh"
 #endif
 #include "elementwise.cuh"
 #include "embed.cuh"
@@ -181,6 +183,9 @@ int check_ws(const void* ws, size_t ws_bytes, const char* who) {
   return 0;
 }
 
+#ifdef CID_ATTN_TRACE
+long long* g_attn_trace = nullptr;       // debug builds only (tools/trace_attn.py)
+#endif
 int d_pad_for(int d) {
   if (d <= 0 || d % 8) return -1;
   if (d <= 32) return 32;
@@ -204,14 +209,21 @@ int launch_attn_self(const CUtensorMap& q, const CUtensorMap& k, const CUtensorM
   return 0;
 }
 #else
+#if defined(CID_ATTN_V4)
+#define CID_ATTN_KERNEL attn_self4_kernel
+template <int D_PAD> using AttnSelfCfg = Attn2Cfg<D_PAD>;
+#else
+#define CID_ATTN_KERNEL attn_self5_kernel
+template <int D_PAD> using AttnSelfCfg = Attn5Cfg<D_PAD>;
+#endif
 template <int D_PAD, int BF>
 int launch_attn_self_t(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
-  using C = Attn2Cfg<D_PAD>;
+  using C = AttnSelfCfg<D_PAD>;
   static bool configured[MAX_DEVICES] = {};
-  if (int rc = set_smem(attn_self4_kernel<D_PAD, BF>, C::TOTAL, "attn_self4_kernel", configured)) return rc;
+  if (int rc = set_smem(CID_ATTN_KERNEL<D_PAD, BF>, C::TOTAL, "attn_self_kernel", configured)) return rc;
   dim3 grid((a.Nq + 127) / 128, a.H, a.B);
-  launch_pdl(attn_self4_kernel<D_PAD, BF>, dim3(grid), dim3(ATTN_THREADS), C::TOTAL, st, q, k, v, a);
-  CID_CHECK_LAUNCH("attn_self4_kernel");
+  launch_pdl(CID_ATTN_KERNEL<D_PAD, BF>, dim3(grid), dim3(ATTN_THREADS), C::TOTAL, st, q, k, v, a);
+  CID_CHECK_LAUNCH("attn_self_kernel");
   return 0;
 }
 template <int D_PAD>
@@ -359,6 +371,9 @@ static int attn_self_impl(const void* Q, long long q_pitch, const void* K, long 
   if ((rc = map_qk(&tk, K, B, N, H, d, k_pitch, 128))) return rc;
   AttnArgs a{}; a.B = B; a.H = H; a.Nq = N; a.Nkv = n_valid; a.d = d; a.scale_log2 = 1.4426950408889634f / sqrtf(float(d));
   a.O = O; a.ldo = ldo; a.is_bf16 = dtype == CID_BF16;
+#ifdef CID_ATTN_TRACE
+  a.trace = g_attn_trace;
+#endif
   if ((rc = map_vt(&tv, Vt, B * H, d, N, dp))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (dp) {
@@ -371,6 +386,10 @@ static int attn_self_impl(const void* Q, long long q_pitch, const void* K, long 
   }
   return fail(CID_ERR_UNSUPPORTED, "cid_attn_self: no instantiation for padded head dim %d", dp);
 }
+
+#ifdef CID_ATTN_TRACE
+int cid_debug_set_attn_trace(long long* buf) { g_attn_trace = buf; return 0; }
+#endif
 
 int cid_attn_cross(const void* Q, long long q_pitch, const void* Kcat, const void* Vtcat, void* O, long long ldo, int B, int H,
                    int N, int d, int n_text, int n_ip, float ip_scale, int dtype, void* stream) {
@@ -453,12 +472,15 @@ int cid_gn_apply_ch(const void* x1, int C1, const float* sums1, const void* x2, 
 }
 int cid_layernorm(const void* x, const void* gamma, const void* beta, void* y, long long rows, int C, float eps, int dtype, void* stream) {
   if (!x || !gamma || !beta || !y || C % 8 || C > 2048) return fail(CID_ERR_ARG, "cid_layernorm: C=%d must be a multiple of 8 and <= 2048", C);
-  const int rows_per_block = 8;
-  const unsigned grid = (unsigned)((rows + rows_per_block - 1) / rows_per_block);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int maxv = (C / 8 + 31) / 32;
-#define CID_LN(MV) launch_pdl(layernorm_kernel<MV>, dim3(grid), dim3(256), 0, st, (const uint16_t*)x, (const uint16_t*)gamma, (const uint16_t*)beta, (uint16_t*)y, rows, C, eps, int(dtype == CID_BF16))
-  if (maxv <= 1) CID_LN(1); else if (maxv <= 2) CID_LN(2); else if (maxv <= 3) CID_LN(3); else if (maxv <= 5) CID_LN(5); else CID_LN(8);
+  const int V = C / 8;
+  const int lpr = V <= 40 ? 8 : (V <= 80 ? 16 : 32);
+  const long long groups = (rows + (32 / lpr) - 1) / (32 / lpr);                 // warp-iterations
+  long long blocks = (groups + 7) / 8;
+  const long long cap = 148LL * 3;                                                 // 3 resident 256-thread blocks per SM, warps loop
+  const unsigned grid = (unsigned)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+#define CID_LN(L, P) launch_pdl(layernorm_kernel<L, P>, dim3(grid), dim3(256), 0, st, (const uint16_t*)x, (const uint16_t*)gamma, (const uint16_t*)beta, (uint16_t*)y, rows, C, eps, int(dtype == CID_BF16))
+  if (lpr == 8) CID_LN(8, 5); else if (lpr == 16) CID_LN(16, 5); else CID_LN(32, 8);
 #undef CID_LN
   CID_CHECK_LAUNCH("layernorm_kernel");
   return 0;

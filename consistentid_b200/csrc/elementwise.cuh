@@ -7,7 +7,9 @@
 
 namespace cid {
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// x * sigmoid(x) with one MUFU.EX2 + one MUFU.RCP (the IEEE division of `x / (1 + e)` costs ~10 extra instructions per element and made
+// the GroupNorm+SiLU pass ALU-bound: 21 M elements per level-0 tensor); relative error ~2 ulp of fp32, far below the 16-bit output rounding
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8], int bf) {
   float2 a = unpack16(u.x, bf), b = unpack16(u.y, bf), c = unpack16(u.z, bf), d = unpack16(u.w, bf);
@@ -78,6 +80,48 @@ gn_stats_kernel(const uint16_t* __restrict__ x1, int C1, const uint16_t* __restr
   }
 }
 
+// Streaming part of the GroupNorm apply kernels: y = [silu](x * scale[c] + shift[c]) over one sample, per-channel affine in smem
+// (aff[0..C) scale, aff[C..2C) shift).  Four 16-byte loads are in flight per thread before the first one is consumed.
+__device__ __forceinline__ void gn_stream(const uint16_t* __restrict__ x1n, int C1, const uint16_t* __restrict__ x2n, int C2,
+                                          uint16_t* __restrict__ yn, const float* aff, long long per_sample, int do_silu, int bf) {
+  const int C = C1 + C2;
+  const unsigned V = unsigned(C / 8), n = unsigned(per_sample);            // (a sample has < 2^32 vectors: 32-bit index math)
+  const unsigned stride = gridDim.x * blockDim.x;
+  constexpr int U = 4;
+  for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += U * stride) {
+    uint4 u[U];
+    int c0[U];
+    size_t pix[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const unsigned i = i0 + k * stride;
+      if (i < n && i >= i0) {
+        const unsigned px = i / V;
+        pix[k] = px;
+        c0[k] = int(i - px * V) * 8;
+        u[k] = (c0[k] < C1) ? *reinterpret_cast<const uint4*>(x1n + pix[k] * C1 + c0[k])
+                            : *reinterpret_cast<const uint4*>(x2n + pix[k] * C2 + (c0[k] - C1));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      if (i0 + k * stride < n && i0 + k * stride >= i0) {
+        float f[8]; unpack8(u[k], f, bf);
+        const float4 s0 = *reinterpret_cast<const float4*>(aff + c0[k]), s1 = *reinterpret_cast<const float4*>(aff + c0[k] + 4);
+        const float4 h0 = *reinterpret_cast<const float4*>(aff + C + c0[k]), h1 = *reinterpret_cast<const float4*>(aff + C + c0[k] + 4);
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float v = fmaf(f[e], sc[e], sh[e]);
+          f[e] = do_silu ? silu_f(v) : v;
+        }
+        *reinterpret_cast<uint4*>(yn + pix[k] * C + c0[k]) = pack8(f, bf);
+      }
+    }
+  }
+}
+
 // y = [silu]((x - mean) * rstd * gamma + beta), x = cat([x1, x2]) NHWC -> y NHWC with C = C1 + C2 channels
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const uint16_t* __restrict__ x1, int C1, const uint16_t* __restrict__ x2, int C2, int HW, int groups,
@@ -107,24 +151,7 @@ gn_apply_kernel(const uint16_t* __restrict__ x1, int C1, const uint16_t* __restr
   const uint16_t* x1n = x1 + (size_t)n * HW * C1;
   const uint16_t* x2n = x2 ? x2 + (size_t)n * HW * C2 : nullptr;
   uint16_t* yn = y + (size_t)n * HW * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample; i += (long long)gridDim.x * blockDim.x) {
-    const int vec = int(i % V);
-    const long long pix = i / V;
-    const int c0 = vec * 8;
-    const uint4 u = (c0 < C1) ? *reinterpret_cast<const uint4*>(x1n + pix * C1 + c0)
-                              : *reinterpret_cast<const uint4*>(x2n + pix * C2 + (c0 - C1));
-    float f[8]; unpack8(u, f, bf);
-    const float4 s0 = *reinterpret_cast<const float4*>(aff + c0), s1 = *reinterpret_cast<const float4*>(aff + c0 + 4);
-    const float4 h0 = *reinterpret_cast<const float4*>(aff + C + c0), h1 = *reinterpret_cast<const float4*>(aff + C + c0 + 4);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float v = fmaf(f[k], sc[k], sh[k]);
-      f[k] = do_silu ? silu_f(v) : v;
-    }
-    *reinterpret_cast<uint4*>(yn + pix * C + c0) = pack8(f, bf);
-  }
+  gn_stream(x1n, C1, x2n, C2, yn, aff, per_sample, do_silu, bf);
 }
 
 // Same apply, statistics given PER CHANNEL by the producers' epilogues (gemm_tc2.cuh "fused GroupNorm statistics"): sums1[n, c, {sum, sumsq}]
@@ -165,74 +192,67 @@ gn_apply_ch_kernel(const uint16_t* __restrict__ x1, int C1, const float* __restr
   const uint16_t* x1n = x1 + (size_t)n * HW * C1;
   const uint16_t* x2n = x2 ? x2 + (size_t)n * HW * C2 : nullptr;
   uint16_t* yn = y + (size_t)n * HW * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample; i += (long long)gridDim.x * blockDim.x) {
-    const int vec = int(i % V);
-    const long long pix = i / V;
-    const int c0 = vec * 8;
-    const uint4 u = (c0 < C1) ? *reinterpret_cast<const uint4*>(x1n + pix * C1 + c0)
-                              : *reinterpret_cast<const uint4*>(x2n + pix * C2 + (c0 - C1));
-    float f[8]; unpack8(u, f, bf);
-    const float4 s0 = *reinterpret_cast<const float4*>(aff + c0), s1 = *reinterpret_cast<const float4*>(aff + c0 + 4);
-    const float4 h0 = *reinterpret_cast<const float4*>(aff + C + c0), h1 = *reinterpret_cast<const float4*>(aff + C + c0 + 4);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float v = fmaf(f[k], sc[k], sh[k]);
-      f[k] = do_silu ? silu_f(v) : v;
-    }
-    *reinterpret_cast<uint4*>(yn + pix * C + c0) = pack8(f, bf);
-  }
+  gn_stream(x1n, C1, x2n, C2, yn, aff, per_sample, do_silu, bf);
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
-// one warp per row, C <= 2048, C % 8 == 0; MAXV = ceil(C / 256) vectors per lane (templated: registers -> occupancy,
-// the kernel is a latency-bound streaming pass)
-template <int MAXV>
-__global__ void __launch_bounds__(256)
+// LPR lanes share a row (8 / 16 / 32 for C <= 320 / 640 / 2048), i.e. a warp normalises 32 / LPR rows at once and every lane has up to VPL
+// independent 16-byte loads in flight (5 for the UNet widths 320 / 640 / 1280) - the one-row-per-warp first version had at most two and ran
+// at 40 % of the HBM bandwidth.  Warps loop over row groups (grid-stride).  Two-pass variance in fp32.
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256, 3)
 layernorm_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ gamma, const uint16_t* __restrict__ beta,
                  uint16_t* __restrict__ y, long long rows, int C, float eps, int bf) {
   griddep_wait();                  // PDL (no-op for a normal launch)
+  constexpr int RPW = 32 / LPR;                                   // rows per warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (row >= rows) return;
+  const int sub = lane % LPR, rsel = lane / LPR;
   const int V = C / 8;
-  float f[MAXV][8];
-  float s = 0.f;
+  const float inv_c = 1.f / float(C);
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5) * RPW;
+  for (long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * RPW + rsel; row < rows; row += wstride) {   // (rsel keeps LPR-groups together)
+    float f[VPL][8];
+    uint4 u[VPL];
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
-    const int v = lane + j * 32;
-    if (v < V) {
-      unpack8(*reinterpret_cast<const uint4*>(x + row * C + v * 8), f[j], bf);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s += f[j][k];
+    for (int j = 0; j < VPL; ++j) {
+      const int v = sub + j * LPR;
+      if (v < V) u[j] = *reinterpret_cast<const uint4*>(x + row * C + v * 8);
     }
-  }
+    float s = 0.f;
 #pragma unroll
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / C;
-  float q = 0.f;
+    for (int j = 0; j < VPL; ++j) {
+      const int v = sub + j * LPR;
+      if (v < V) {
+        unpack8(u[j], f[j], bf);
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
-    const int v = lane + j * 32;
-    if (v < V) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { const float d = f[j][k] - mean; q += d * d; }
+        for (int k = 0; k < 8; ++k) s += f[j][k];
+      }
     }
-  }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / C + eps);
+    for (int o = LPR / 2; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_c;
+    float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
-    const int v = lane + j * 32;
-    if (v < V) {
-      float ga[8], be[8], o8[8];
-      unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), ga, bf);
-      unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), be, bf);
+    for (int j = 0; j < VPL; ++j) {
+      const int v = sub + j * LPR;
+      if (v < V) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o8[k] = (f[j][k] - mean) * rstd * ga[k] + be[k];
-      *reinterpret_cast<uint4*>(y + row * C + v * 8) = pack8(o8, bf);
+        for (int k = 0; k < 8; ++k) { const float d = f[j][k] - mean; q += d * d; }
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * inv_c + eps);
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int v = sub + j * LPR;
+      if (v < V) {
+        float g8[8], b8[8], o8[8];                        // gamma / beta: a few hundred bytes, L1-resident after the first row group
+        unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + v * 8)), g8, bf); unpack8(__ldg(reinterpret_cast<const uint4*>(beta + v * 8)), b8, bf);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o8[k] = (f[j][k] - mean) * rstd * g8[k] + b8[k];
+        *reinterpret_cast<uint4*>(y + row * C + v * 8) = pack8(o8, bf);
+      }
     }
   }
 }
