@@ -18,6 +18,10 @@
 #include "attn_tc4.cuh"          // A/B builds only: chunk-pipelined softmax, single P buffer
 #else
 #include "attn_tc5.cuh"
+#ifndef CID_ATTN_NO_V6
+#include "attn_tc6.cuh"
+#define CID_ATTN_V6 1
+#endif
 #endif
 #include "elementwise.cuh"
 #include "embed.cuh"
@@ -226,8 +230,26 @@ int launch_attn_self_t(const CUtensorMap& q, const CUtensorMap& k, const CUtenso
   CID_CHECK_LAUNCH("attn_self_kernel");
   return 0;
 }
+#ifdef CID_ATTN_V6
+// two 128-row query tiles per CTA, P in tensor memory, ping-pong softmax warpgroups (attn_tc6.cuh): head dims <= 80, >= 256 queries
+template <int D_PAD, int BF>
+int launch_attn_self6_t(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
+  using C = Attn6Cfg<D_PAD>;
+  static bool configured[MAX_DEVICES] = {};
+  if (int rc = set_smem(attn_self6_kernel<D_PAD, BF>, C::TOTAL, "attn_self6_kernel", configured)) return rc;
+  dim3 grid((a.Nq + 255) / 256, a.H, a.B);
+  launch_pdl(attn_self6_kernel<D_PAD, BF>, dim3(grid), dim3(ATTN6_THREADS), C::TOTAL, st, q, k, v, a);
+  CID_CHECK_LAUNCH("attn_self6_kernel");
+  return 0;
+}
+#endif
 template <int D_PAD>
 int launch_attn_self(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
+#ifdef CID_ATTN_V6
+  if constexpr (D_PAD <= 80) {
+    if (a.Nq >= 256) return a.is_bf16 ? launch_attn_self6_t<D_PAD, 1>(q, k, v, a, st) : launch_attn_self6_t<D_PAD, 0>(q, k, v, a, st);
+  }
+#endif
   return a.is_bf16 ? launch_attn_self_t<D_PAD, 1>(q, k, v, a, st) : launch_attn_self_t<D_PAD, 0>(q, k, v, a, st);
 }
 #endif

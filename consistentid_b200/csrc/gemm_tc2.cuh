@@ -5,7 +5,7 @@
 //   warp 0      TMA producer - keeps the STAGES-deep smem ring full ACROSS tile boundaries
 //   warp 1      TMEM allocator (512 columns = two accumulators) + tcgen05.mma issuer; alternates accumulators so the
 //               main loop of tile i+1 overlaps the epilogue of tile i
-//   warps 2-9   epilogue: two warps per TMEM lane quarter, each draining half of the tile's columns in 16-column
+//   warps 2-17  epilogue: four warps per TMEM lane quarter, each draining a quarter of the tile's columns in 16-column
 //               tcgen05.ld chunks; residual rows are prefetched into registers BEFORE waiting for the accumulator and the
 //               bias slice of the tile is staged once in smem, so no global-load latency sits between TMEM and the stores
 //
@@ -22,8 +22,13 @@
 
 namespace cid {
 
-constexpr int GEMM2_THREADS = 320;
-constexpr int GEMM2_EPI_THREADS = 256;
+// 16 epilogue warps: four per TMEM lane quarter, each draining a quarter of the tile's columns.  The epilogue of the small-K GEMMs is
+// latency-bound (ncu, profiles/r02_ncu_outproj_sd15_*: IPC 0.07 per warp - residual loads, TMEM loads, instruction fetch), not issue-bound:
+// with eight warps (two per scheduler) a 128 x 160 tile took ~14 k cycles against 1.7 k of tensor work.
+constexpr int GEMM2_EPI_WARPS = 16;
+constexpr int GEMM2_EPI_THREADS = GEMM2_EPI_WARPS * 32;
+constexpr int GEMM2_THREADS = 64 + GEMM2_EPI_THREADS;
+constexpr int GEMM2_PARTS = GEMM2_EPI_WARPS / 4;            // column ranges per lane quarter
 
 template <int BN, int STAGES>
 struct Gemm2Smem {
@@ -37,7 +42,7 @@ struct Gemm2Smem {
   static constexpr int TOTAL = STAT_OFF + 2 * 2 * BN * 4 + 1024;
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(GEMM2_EPI_THREADS) : "memory"); }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -225,17 +230,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     constexpr int bf = BF;
     const int ew = warp - 2;
     const int quarter = warp & 3;
-    const int half = ew >> 2;                              // which half of the tile's columns this warp drains
+    const int part = ew >> 2;                              // which share of the tile's columns this warp drains (GEMM2_PARTS per lane quarter)
     const int r = quarter * 32 + lane;
-    const int et = threadIdx.x - 64;                       // 0..255
+    const int et = threadIdx.x - 64;                       // 0 .. GEMM2_EPI_THREADS - 1
     constexpr bool geglu = EPI == EPI_GEGLU;
     // column range [c_beg, c_end) in 16-column chunks (GEGLU: over the value half only)
     constexpr int NCHUNK = BN / 16;
     constexpr int NCHUNK_G = (BN / 2) / 16 > 0 ? (BN / 2) / 16 : 1;
     const int nch = geglu ? NCHUNK_G : NCHUNK;
-    const int ch_beg = half == 0 ? 0 : (nch + 1) / 2;
-    const int ch_end = half == 0 ? (nch + 1) / 2 : nch;
-    constexpr int MAXCH = (NCHUNK + 1) / 2;
+    const int ch_beg = part * nch / GEMM2_PARTS;
+    const int ch_end = (part + 1) * nch / GEMM2_PARTS;
+    constexpr int MAXCH = (NCHUNK + GEMM2_PARTS - 1) / GEMM2_PARTS;
     // global row of this thread's accumulator row in tile `tile_`
     auto my_row = [&](int tile_, long long& grow_) -> bool {
       const int mt_ = tile_ / n_tiles;

@@ -24,9 +24,10 @@ e0.record(); ops.attn_self(qk[:, :C], qk[:, C:], vt, o, NB, H, N, d); e1.record(
 print(f"{model}: kernel {e0.elapsed_time(e1) * 1e3:.0f} us")
 t = trace.cpu().view(64, 64, 8)
 T = N // 128
-names = ["wait S", "ld S", "max", "wait Pbuf", "exp+st", "arrive"]
-print("cta smid | per-tile period | " + " | ".join(names))
-for cta in range(0, min(32, N // 128), 4):
+# v5: rows = CTAs (one 128-query tile each); v6: rows = (CTA, warpgroup) pairs (two tiles per CTA) and phase 3->4 is the wait for the MUFU token
+names = ["wait S", "ld S", "max", "wait Pbuf/token", "exp", "st P + arrive"]
+print("row smid | per-tile period | " + " | ".join(names))
+for cta in list(range(0, 8)) + list(range(8, min(32, N // 128), 4)):
     tt = t[cta, :T]
     smid = int(t[cta, 0, 7])
     ph = [(tt[2:, k + 1] - tt[2:, k]).float().mean().item() for k in range(6)]
