@@ -12,16 +12,10 @@
 
 #include "../../include/cidb200.h"
 #include "attn_cross.cuh"
-#if defined(CID_ATTN_V3)
-#include "attn_tc3.cuh"          // A/B builds only (tools/build_variant.sh): the round-1 kernel
-#elif defined(CID_ATTN_V4)
-#include "attn_tc4.cuh"          // A/B builds only: chunk-pipelined softmax, single P buffer
-#else
-#include "attn_tc5.cuh"
+#include "attn_tc5.cuh"           // one 128-row query tile per CTA: head dims > 80 and short sequences
 #ifndef CID_ATTN_NO_V6
-#include "attn_tc6.cuh"
+#include "attn_tc6.cuh"           // two query tiles per CTA, P in tensor memory: head dims <= 80, >= 256 queries
 #define CID_ATTN_V6 1
-#endif
 #endif
 #include "elementwise.cuh"
 #include "embed.cuh"
@@ -201,33 +195,14 @@ int d_pad_for(int d) {
   return -1;
 }
 
-#ifdef CID_ATTN_V3
-template <int D_PAD>
-int launch_attn_self(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
-  using C = Attn2Cfg<D_PAD>;
-  static bool configured[MAX_DEVICES] = {};
-  if (int rc = set_smem(attn_self3_kernel<D_PAD>, C::TOTAL, "attn_self3_kernel", configured)) return rc;
-  dim3 grid((a.Nq + 127) / 128, a.H, a.B);
-  launch_pdl(attn_self3_kernel<D_PAD>, dim3(grid), dim3(ATTN_THREADS), C::TOTAL, st, q, k, v, a);
-  CID_CHECK_LAUNCH("attn_self3_kernel");
-  return 0;
-}
-#else
-#if defined(CID_ATTN_V4)
-#define CID_ATTN_KERNEL attn_self4_kernel
-template <int D_PAD> using AttnSelfCfg = Attn2Cfg<D_PAD>;
-#else
-#define CID_ATTN_KERNEL attn_self5_kernel
-template <int D_PAD> using AttnSelfCfg = Attn5Cfg<D_PAD>;
-#endif
 template <int D_PAD, int BF>
 int launch_attn_self_t(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
-  using C = AttnSelfCfg<D_PAD>;
+  using C = Attn5Cfg<D_PAD>;
   static bool configured[MAX_DEVICES] = {};
-  if (int rc = set_smem(CID_ATTN_KERNEL<D_PAD, BF>, C::TOTAL, "attn_self_kernel", configured)) return rc;
+  if (int rc = set_smem(attn_self5_kernel<D_PAD, BF>, C::TOTAL, "attn_self5_kernel", configured)) return rc;
   dim3 grid((a.Nq + 127) / 128, a.H, a.B);
-  launch_pdl(CID_ATTN_KERNEL<D_PAD, BF>, dim3(grid), dim3(ATTN_THREADS), C::TOTAL, st, q, k, v, a);
-  CID_CHECK_LAUNCH("attn_self_kernel");
+  launch_pdl(attn_self5_kernel<D_PAD, BF>, dim3(grid), dim3(ATTN5_THREADS), C::TOTAL, st, q, k, v, a);
+  CID_CHECK_LAUNCH("attn_self5_kernel");
   return 0;
 }
 #ifdef CID_ATTN_V6
@@ -252,7 +227,6 @@ int launch_attn_self(const CUtensorMap& q, const CUtensorMap& k, const CUtensorM
 #endif
   return a.is_bf16 ? launch_attn_self_t<D_PAD, 1>(q, k, v, a, st) : launch_attn_self_t<D_PAD, 0>(q, k, v, a, st);
 }
-#endif
 template <int D_PAD>
 int launch_attn_cross(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
   using C = CrossCfg<D_PAD>;

@@ -57,28 +57,36 @@ attn_cross_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const uint32_t tmem_S = tmem, tmem_Ot = tmem, tmem_Oi = tmem + D_PAD;      // O_* overwrite S after the softmax has read it
   griddep_wait();                  // PDL: the prologue above overlaps the predecessor's tail
 
-  if (warp == 0 && lane == 0) {
-    mbar_expect_tx(bar_ld, C::Q_BYTES + C::K_BYTES + C::V_BYTES);
-    for (int ch = 0; ch < C::NCH; ++ch) {
-      tma_load_4d(sbase + ch * 16384, &tmQ, bar_ld, ch * 64, q0, h, b);
-      tma_load_4d(sbase + C::OFF_K + ch * C::K_CHUNK, &tmK, bar_ld, ch * 64, 0, h, b);
+  // warp 0 (converged; single-thread instructions under elect_one(), see gemm_tc2.cuh) loads Q, K_cat, V_cat^T and issues S = Q K_cat^T
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_ld, C::Q_BYTES + C::K_BYTES + C::V_BYTES);
+#pragma unroll
+      for (int ch = 0; ch < C::NCH; ++ch) {
+        tma_load_4d(sbase + ch * 16384, &tmQ, bar_ld, ch * 64, q0, h, b);
+        tma_load_4d(sbase + C::OFF_K + ch * C::K_CHUNK, &tmK, bar_ld, ch * 64, 0, h, b);
+      }
+#pragma unroll
+      for (int kc = 0; kc < 2; ++kc) tma_load_3d(sbase + C::OFF_V + kc * C::V_CHUNK, &tmVt, bar_ld, kc * 64, 0, b * a.H + h);
+      griddep_launch_dependents();
     }
-    for (int kc = 0; kc < 2; ++kc) tma_load_3d(sbase + C::OFF_V + kc * C::V_CHUNK, &tmVt, bar_ld, kc * 64, 0, b * a.H + h);
-    griddep_launch_dependents();
+    __syncwarp();
     mbar_wait(bar_ld, 0);
     tc_fence_after();
     const uint32_t idesc_s = make_idesc(128, C::KROWS, a.is_bf16);
+    if (elect_one()) {
 #pragma unroll
-    for (int ch = 0; ch < C::NCH; ++ch) {
-      const int ksteps = (D_PAD - ch * 64 >= 64) ? 4 : (D_PAD - ch * 64) / 16;
+      for (int ch = 0; ch < C::NCH; ++ch) {
+        const int ksteps = (D_PAD - ch * 64 >= 64) ? 4 : (D_PAD - ch * 64) / 16;
 #pragma unroll
-      for (int kk = 0; kk < ksteps; ++kk)
-        umma_ss(tmem_S, make_desc_sw128(sbase + ch * 16384 + kk * 32),
-                make_desc_sw128(sbase + C::OFF_K + ch * C::K_CHUNK + kk * 32), idesc_s, (ch | kk) ? 1u : 0u);
+        for (int kk = 0; kk < ksteps; ++kk)
+          umma_ss(tmem_S, make_desc_sw128(sbase + ch * 16384 + kk * 32),
+                  make_desc_sw128(sbase + C::OFF_K + ch * C::K_CHUNK + kk * 32), idesc_s, (ch | kk) ? 1u : 0u);
+      }
+      umma_commit(bar_s);
     }
-    umma_commit(bar_s);
+    __syncwarp();
   }
-  __syncwarp();
 
   const int r = warp * 32 + lane;
   const uint32_t lane_off = uint32_t(warp * 32) << 16;
@@ -131,25 +139,25 @@ attn_cross_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     tc_fence_after();
     const uint32_t idesc_pv = make_idesc(128, D_PAD, a.is_bf16);
     const uint32_t sp0 = sbase + C::OFF_P0, sp1 = sbase + C::OFF_P1, sv = sbase + C::OFF_V;
     // text range: keys [0, 80) = 5 k-steps (rows 77..79 of K_cat / V_cat are zero padding, P is 0 there); with no id tokens
     // (plain cross-attention, e.g. ControlNet's default processor over all 81 rows) the text range spans all 96 rows
-    const int tsteps = (a.n_ip > 0) ? 5 : 6;
+    const bool has_ip = a.n_ip > 0;
+    if (elect_one()) {
 #pragma unroll
-    for (int ks = 0; ks < 6; ++ks) {
-      if (ks < tsteps) {
+      for (int ks = 0; ks < 5; ++ks) {
         const int kc = ks >> 2, kk = ks & 3;
         umma_ss(tmem_Ot, make_desc_sw128((kc ? sp1 : sp0) + kk * 32), make_desc_sw128(sv + kc * C::V_CHUNK + kk * 32), idesc_pv, ks ? 1u : 0u);
       }
+      // keys [80, 96) = k-step 5 (chunk 1, second 16-key slice): the id range (own accumulator) or, without id tokens, more text keys
+      umma_ss(has_ip ? tmem_Oi : tmem_Ot, make_desc_sw128(sp1 + 32), make_desc_sw128(sv + C::V_CHUNK + 32), idesc_pv, has_ip ? 0u : 1u);
+      umma_commit(bar_o);
     }
-    // id range: keys [80, 96) = k-step 5 (chunk 1, second 16-key slice)
-    if (a.n_ip > 0) umma_ss(tmem_Oi, make_desc_sw128(sp1 + 32), make_desc_sw128(sv + C::V_CHUNK + 32), idesc_pv, 0u);
-    umma_commit(bar_o);
+    __syncwarp();
   }
-  __syncwarp();
   mbar_wait(bar_o, 0);
   tc_fence_after();
   const float wt = 1.f / lt;

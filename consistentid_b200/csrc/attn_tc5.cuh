@@ -55,8 +55,10 @@ struct Attn5Cfg {
   static constexpr int MIN_CTAS = SMALL ? 2 : 1;
 };
 
+constexpr int ATTN5_THREADS = 224;       // warp 0 TMA (Q, K), warp 1 MMA, warps 2-5 softmax, warp 6 TMA (V^T)
+
 template <int D_PAD, int BF>
-__global__ void __launch_bounds__(ATTN_THREADS, Attn5Cfg<D_PAD>::MIN_CTAS)
+__global__ void __launch_bounds__(ATTN5_THREADS, Attn5Cfg<D_PAD>::MIN_CTAS)
 attn_self5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmVt, const AttnArgs a) {
   using C = Attn5Cfg<D_PAD>;
@@ -104,32 +106,44 @@ attn_self5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const uint32_t tmem_S = tmem, tmem_O = tmem + 128, tmem_L = tmem + 128 + D_PAD;
   griddep_wait();                  // PDL: the prologue above overlaps the predecessor's tail
 
+  // Producer / issuer warps are WARP-CONVERGED with the single-thread instructions under elect_one() (see gemm_tc2.cuh).
   if (warp == 0) {
-    // ============================================================ TMA producers: lane 0 streams K (and Q), lane 1 streams V^T.
-    // Separate threads so that a K tile never queues behind the V tile of the previous key block (whose buffer is only released when
-    // P.V retires, late in the tile): with one producer thread S_{j+1} = Q K_{j+1}^T was ~500 cycles late at every tile boundary.
-    if (lane == 0) {
+    // ============================================================ TMA producer: Q, then the K stream
+    if (elect_one()) {
       mbar_expect_tx(q_full, C::Q_BYTES);
+#pragma unroll
       for (int ch = 0; ch < C::NCH; ++ch) tma_load_4d(sbase + ch * 16384, &tmQ, q_full, ch * 64, q0, h, b);
-      int stage = 0; uint32_t phase = 0;
-      for (int j = 0; j < T; ++j) {
-        mbar_wait(k_empty(stage), phase ^ 1u);
-        mbar_expect_tx(k_full(stage), C::K_BYTES);
-        for (int ch = 0; ch < C::NCH; ++ch)
-          tma_load_4d(sbase + C::OFF_K + stage * C::K_BYTES + ch * 16384, &tmK, k_full(stage), ch * 64, j * 128, h, b);
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-      }
-    } else if (lane == 1) {
-      int stage = 0; uint32_t phase = 0;
-      for (int j = 0; j < T; ++j) {
-        mbar_wait(v_empty(stage), phase ^ 1u);
-        mbar_expect_tx(v_full(stage), C::V_BYTES);
-        for (int kc = 0; kc < 2; ++kc)
-          tma_load_3d(sbase + C::OFF_V + stage * C::V_BYTES + kc * C::V_CHUNK, &tmVt, v_full(stage), j * 128 + kc * 64, 0, b * a.H + h);
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-      }
-      griddep_launch_dependents();
     }
+    __syncwarp();
+    int stage = 0; uint32_t phase = 0;
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(k_empty(stage), phase ^ 1u);
+      const uint32_t kb = k_full(stage), dst = sbase + C::OFF_K + stage * C::K_BYTES;
+      if (elect_one()) {
+        mbar_expect_tx(kb, C::K_BYTES);
+#pragma unroll
+        for (int ch = 0; ch < C::NCH; ++ch) tma_load_4d(dst + ch * 16384, &tmK, kb, ch * 64, j * 128, h, b);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 6) {
+    // ============================================================ TMA producer: the V^T stream (own warp: a K tile must never queue behind
+    // the V tile of the previous key block, whose buffer is only released when P.V retires, late in the tile)
+    int stage = 0; uint32_t phase = 0;
+    const int bh = b * a.H + h;
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(v_empty(stage), phase ^ 1u);
+      const uint32_t vb = v_full(stage), dst = sbase + C::OFF_V + stage * C::V_BYTES;
+      if (elect_one()) {
+        mbar_expect_tx(vb, C::V_BYTES);
+        tma_load_3d(dst, &tmVt, vb, j * 128, 0, bh);
+        tma_load_3d(dst + C::V_CHUNK, &tmVt, vb, j * 128 + 64, 0, bh);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    }
+    if (elect_one()) griddep_launch_dependents();
     __syncwarp();
   } else if (warp == 1) {
     // ============================================================ MMA issuer
@@ -140,39 +154,44 @@ attn_self5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t q_lo = desc_lo(sbase), k_lo = desc_lo(sbase + C::OFF_K), v_lo = desc_lo(sbase + C::OFF_V), p_lo = desc_lo(sbase + C::OFF_P);
     auto issue_S = [&](int stage) {
       const uint32_t kl = k_lo + uint32_t(stage * C::K_BYTES) / 16;
+      const uint32_t ke = k_empty(stage);
+      if (elect_one()) {
 #pragma unroll
-      for (int ch = 0; ch < C::NCH; ++ch) {
-        const int ksteps = (D_PAD - ch * 64 >= 64) ? 4 : (D_PAD - ch * 64) / 16;
+        for (int ch = 0; ch < C::NCH; ++ch) {
+          const int ksteps = (D_PAD - ch * 64 >= 64) ? 4 : (D_PAD - ch * 64) / 16;
 #pragma unroll
-        for (int kk = 0; kk < ksteps; ++kk)
-          umma_ss(tmem_S, desc_make(q_lo + ch * 1024 + kk * 2), desc_make(kl + ch * 1024 + kk * 2), idesc_s, (ch | kk) ? 1u : 0u);
+          for (int kk = 0; kk < ksteps; ++kk)
+            umma_ss(tmem_S, desc_make(q_lo + ch * 1024 + kk * 2), desc_make(kl + ch * 1024 + kk * 2), idesc_s, (ch | kk) ? 1u : 0u);
+        }
+        umma_commit(s_full);
+        umma_commit(ke);
       }
+      __syncwarp();
     };
     mbar_wait(q_full, 0);
     int stage = 0; uint32_t phase = 0;
     int nstage = 0; uint32_t nphase = 0;
     mbar_wait(k_full(0), 0);
     tc_fence_after();
-    if (lane == 0) { issue_S(0); umma_commit(s_full); umma_commit(k_empty(0)); }
-    __syncwarp();
+    issue_S(0);
     if (++nstage == STAGES) { nstage = 0; nphase ^= 1u; }
     for (int j = 0; j < T; ++j) {
       if (j + 1 < T) {
         mbar_wait(k_full(nstage), nphase);
         mbar_wait(s_free, uint32_t(j & 1));              // the softmax warps hold S_j in registers
         tc_fence_after();
-        if (lane == 0) { issue_S(nstage); umma_commit(s_full); umma_commit(k_empty(nstage)); }
-        __syncwarp();
+        issue_S(nstage);
         if (++nstage == STAGES) { nstage = 0; nphase ^= 1u; }
       }
       const int pb = j & 1;
       mbar_wait(p_full(pb), uint32_t((j >> 1) & 1));     // P_j in smem buffer pb, O / l rescaled if needed
       mbar_wait(v_full(stage), phase);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t vl = v_lo + uint32_t(stage * C::V_BYTES) / 16;
-        const uint32_t pl = p_lo + uint32_t(pb * C::P_BYTES) / 16;
-        const uint32_t acc0 = j > 0 ? 1u : 0u;
+      const uint32_t vl = v_lo + uint32_t(stage * C::V_BYTES) / 16;
+      const uint32_t pl = p_lo + uint32_t(pb * C::P_BYTES) / 16;
+      const uint32_t acc0 = j > 0 ? 1u : 0u;
+      const uint32_t pvb = pv_full(pb), veb = v_empty(stage);
+      if (elect_one()) {
 #pragma unroll
         for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
@@ -182,8 +201,8 @@ attn_self5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             umma_ss(tmem_O, pdesc, desc_make(vl + kc * (C::V_CHUNK / 16) + kk * 2), idesc_pv, acc);
             umma_ss(tmem_L, pdesc, ones_desc, idesc_l, acc);
           }
-        umma_commit(pv_full(pb));
-        umma_commit(v_empty(stage));
+        umma_commit(pvb);
+        umma_commit(veb);
       }
       __syncwarp();
       if (++stage == STAGES) { stage = 0; phase ^= 1u; }

@@ -10,9 +10,9 @@
 //     score row in TENSOR MEMORY (tcgen05.st) and P.V takes its A operand from there (tcgen05.mma with A in TMEM);
 //   * V^T tiles carry 16 extra rows of ones, so the same MMA that accumulates O = sum P V also accumulates the row sums l = sum P 1 in the 16
 //     columns next to O (no second pass over P);
-//   * ping-pong: a named-barrier token lets only ONE warpgroup evaluate exponentials at a time; while it does, the other warpgroup's
-//     P.V_j and S_{j+1} = Q K_{j+1}^T run on the tensor pipe and its next score row is loaded and max-reduced.  The MUFU never idles and
-//     nothing ever waits on it behind a barrier.
+//   * the two warpgroups run free: while one waits for its P.V_j / S_{j+1} on the tensor pipe and reloads / max-reduces its next score row,
+//     the other has the MUFU alone; when both are in their exponentials they share it (two warps per scheduler reach 92 % of the MUFU
+//     rate, one warp alone only 67 %, tools/microbench_softmax.cu - which is why a strict ping-pong token, -DCID_ATTN_TOKEN, measured slower).
 // TMEM (512 columns): S0 | S1 (128 fp32 columns each; P_i aliases columns 0..63 of S_i) | O0, l0 | O1, l1 (D_PAD + 16 each).
 // Ordering relies on tcgen05.mma instructions of one thread executing in issue order: P.V_i(j) (reads P_i) is issued before S_i(j+1)
 // (overwrites it), and the commit that signals S_i(j+1) therefore also covers P.V_i(j) - the O / l rescale needs no extra wait.
@@ -35,7 +35,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 constexpr float ATTN_RESCALE_THRESHOLD = 8.0f;      // log2 units: P <= 2^8, exact range of fp16 / bf16
 #endif
 
-constexpr int ATTN6_THREADS = 320;                    // warp 0 TMA, warp 1 MMA, warps 2-5 softmax of query tile 0, warps 6-9 of tile 1
+constexpr int ATTN6_THREADS = 352;                    // warp 0 TMA (Q, K), warp 1 MMA, warps 2-5 softmax of query tile 0, warps 6-9 of tile 1, warp 10 TMA (V^T)
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -107,83 +107,112 @@ attn_self6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const uint32_t tmem = *tmem_slot;
   griddep_wait();                  // PDL: the prologue above overlaps the predecessor's tail
 
+  // Producer / issuer warps are WARP-CONVERGED with the single-thread instructions under elect_one() (see gemm_tc2.cuh: `if (lane == 0)`
+  // regions cost ~90 cycles per tcgen05.mma and ~225 per TMA instruction in R2UR moves and ELECT / BRA.U.ANY retry loops).
   if (warp == 0) {
-    // ============================================================ TMA producers: lane 0 streams Q0, Q1 and K, lane 1 streams V^T
-    if (lane == 0) {
+    // ============================================================ TMA producer: Q0, Q1, then the K stream
+    if (elect_one()) {
       mbar_expect_tx(q_full, 2 * C::Q_BYTES);
       for (int i = 0; i < 2; ++i)
         for (int ch = 0; ch < C::NCH; ++ch) tma_load_4d(sbase + i * C::Q_BYTES + ch * 16384, &tmQ, q_full, ch * 64, q0 + i * 128, h, b);
-      int stage = 0; uint32_t phase = 0;
-      for (int j = 0; j < T; ++j) {
-        mbar_wait(k_empty(stage), phase ^ 1u);
-        mbar_expect_tx(k_full(stage), C::K_BYTES);
-        for (int ch = 0; ch < C::NCH; ++ch)
-          tma_load_4d(sbase + C::OFF_K + stage * C::K_BYTES + ch * 16384, &tmK, k_full(stage), ch * 64, j * 128, h, b);
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-      }
-    } else if (lane == 1) {
-      int stage = 0; uint32_t phase = 0;
-      for (int j = 0; j < T; ++j) {
-        mbar_wait(v_empty(stage), phase ^ 1u);
-        mbar_expect_tx(v_full(stage), C::V_TX);
-        for (int kc = 0; kc < 2; ++kc)
-          tma_load_3d(sbase + C::OFF_V + stage * C::V_BYTES + kc * C::V_CHUNK, &tmVt, v_full(stage), j * 128 + kc * 64, 0, b * a.H + h);
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-      }
-      griddep_launch_dependents();
     }
     __syncwarp();
+    int stage = 0; uint32_t phase = 0;
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(k_empty(stage), phase ^ 1u);
+      const uint32_t kb = k_full(stage), dst = sbase + C::OFF_K + stage * C::K_BYTES;
+      if (elect_one()) {
+        mbar_expect_tx(kb, C::K_BYTES);
+#pragma unroll
+        for (int ch = 0; ch < C::NCH; ++ch) tma_load_4d(dst + ch * 16384, &tmK, kb, ch * 64, j * 128, h, b);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 10) {
+    // ============================================================ TMA producer: the V^T stream (its own warp: a V buffer is released only
+    // when P.V of BOTH query tiles retired, and a K tile must never queue behind that)
+    int stage = 0; uint32_t phase = 0;
+    const int bh = b * a.H + h;
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(v_empty(stage), phase ^ 1u);
+      const uint32_t vb = v_full(stage), dst = sbase + C::OFF_V + stage * C::V_BYTES;
+      if (elect_one()) {
+        mbar_expect_tx(vb, C::V_TX);
+        tma_load_3d(dst, &tmVt, vb, j * 128, 0, bh);
+        tma_load_3d(dst + C::V_CHUNK, &tmVt, vb, j * 128 + 64, 0, bh);
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    }
+    if (elect_one()) griddep_launch_dependents();
+    __syncwarp();
   } else if (warp == 1) {
-    // ============================================================ MMA issuer (one thread)
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc(128, 128, BF);
-      const uint32_t idesc_pv = make_idesc(128, C::VN, BF);
-      const uint32_t q_lo = desc_lo(sbase), k_lo = desc_lo(sbase + C::OFF_K), v_lo = desc_lo(sbase + C::OFF_V);
-      auto issue_S = [&](int i, int stage) {
-        const uint32_t ql = q_lo + uint32_t(i * C::Q_BYTES) / 16, kl = k_lo + uint32_t(stage * C::K_BYTES) / 16;
+    // ============================================================ MMA issuer
+    const uint32_t idesc_s = make_idesc(128, 128, BF);
+    const uint32_t idesc_pv = make_idesc(128, C::VN, BF);
+    const uint32_t q_lo = desc_lo(sbase), k_lo = desc_lo(sbase + C::OFF_K), v_lo = desc_lo(sbase + C::OFF_V);
+    // S_i = Q_i K^T into TMEM columns [i * 128, +128); all operands are warp-uniform values computed by the whole warp
+    auto issue_S = [&](int i, int stage, uint32_t bar_s, uint32_t bar_k, bool release_k) {
+      const uint32_t ql = q_lo + uint32_t(i * C::Q_BYTES) / 16, kl = k_lo + uint32_t(stage * C::K_BYTES) / 16;
+      const uint32_t d_tm = tmem + C::TM_S + i * 128;
+      if (elect_one()) {
 #pragma unroll
         for (int ch = 0; ch < C::NCH; ++ch) {
           const int ksteps = (D_PAD - ch * 64 >= 64) ? 4 : (D_PAD - ch * 64) / 16;
 #pragma unroll
           for (int kk = 0; kk < ksteps; ++kk)
-            umma_ss(tmem + C::TM_S + i * 128, desc_make(ql + ch * 1024 + kk * 2), desc_make(kl + ch * 1024 + kk * 2), idesc_s, (ch | kk) ? 1u : 0u);
+            umma_ss(d_tm, desc_make(ql + ch * 1024 + kk * 2), desc_make(kl + ch * 1024 + kk * 2), idesc_s, (ch | kk) ? 1u : 0u);
         }
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(k_full(0), 0);
-      tc_fence_after();
-      issue_S(0, 0); umma_commit(s_full(0));
-      issue_S(1, 0); umma_commit(s_full(1));
-      umma_commit(k_empty(0));
-      int ks = (STAGES > 1) ? 1 : 0; uint32_t kph = (STAGES > 1) ? 0u : 1u;     // stage / phase of K_{j+1}
-      int vs = 0; uint32_t vph = 0;                                               // stage / phase of V_j
-      for (int j = 0; j < T; ++j) {
-        const bool more = j + 1 < T;
+        umma_commit(bar_s);
+        if (release_k) umma_commit(bar_k);
+      }
+      __syncwarp();
+    };
+#ifdef CID_ATTN_TRACE
+    const bool trm = a.trace != nullptr && blockIdx.y == 0 && blockIdx.z == 0 && blockIdx.x < 16 && lane == 0;
+    auto mstamp = [&](int j_, int e) { if (trm && j_ < 64) a.trace[((size_t)(32 + blockIdx.x) * 64 + j_) * 8 + e] = clock64(); };
+#else
+    auto mstamp = [&](int, int) {};
+#endif
+    mbar_wait(q_full, 0);
+    mbar_wait(k_full(0), 0);
+    tc_fence_after();
+    issue_S(0, 0, s_full(0), 0u, false);
+    issue_S(1, 0, s_full(1), k_empty(0), true);
+    int ks = (STAGES > 1) ? 1 : 0; uint32_t kph = (STAGES > 1) ? 0u : 1u;     // stage / phase of K_{j+1}
+    int vs = 0; uint32_t vph = 0;                                               // stage / phase of V_j
+    for (int j = 0; j < T; ++j) {
+      const bool more = j + 1 < T;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          mbar_wait(p_full(i), uint32_t(j & 1));               // P_i(j) written over S_i, O_i / l_i rescaled if needed
-          if (i == 0) mbar_wait(v_full(vs), vph);
-          tc_fence_after();
-          const uint32_t vl = v_lo + uint32_t(vs * C::V_BYTES) / 16;
-          const uint32_t a_tm = tmem + C::TM_S + i * 128;       // P_i: 64 columns of packed 16-bit pairs, 8 columns per 16-key MMA step
-          const uint32_t d_tm = tmem + C::TM_O + i * C::O_STRIDE;
+      for (int i = 0; i < 2; ++i) {
+        mbar_wait(p_full(i), uint32_t(j & 1));               // P_i(j) written over S_i, O_i / l_i rescaled if needed
+        mstamp(j, i * 3 + 0);
+        if (i == 0) mbar_wait(v_full(vs), vph);
+        tc_fence_after();
+        const uint32_t vl = v_lo + uint32_t(vs * C::V_BYTES) / 16;
+        const uint32_t a_tm = tmem + C::TM_S + i * 128;       // P_i: 64 columns of packed 16-bit pairs, 8 columns per 16-key MMA step
+        const uint32_t d_tm = tmem + C::TM_O + i * C::O_STRIDE;
+        const uint32_t acc0 = j > 0 ? 1u : 0u;
+        const uint32_t ob = o_full(i), vb = v_empty(vs);
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            umma_ts(d_tm, a_tm + kk * 8, desc_make(vl + (kk >> 2) * (C::V_CHUNK / 16) + (kk & 3) * 2), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
-          if (!more) umma_commit(o_full(i));
-          if (i == 1) umma_commit(v_empty(vs));
-          if (more) {
-            if (i == 0) { mbar_wait(k_full(ks), kph); tc_fence_after(); }
-            issue_S(i, ks);                                     // executes after P.V_i(j) (issue order): S_i may overwrite P_i
-            umma_commit(s_full(i));
-            if (i == 1) umma_commit(k_empty(ks));
-          }
+            umma_ts(d_tm, a_tm + kk * 8, desc_make(vl + (kk >> 2) * (C::V_CHUNK / 16) + (kk & 3) * 2), idesc_pv, kk ? 1u : acc0);
+          if (!more) umma_commit(ob);
+          if (i == 1) umma_commit(vb);
         }
-        if (++vs == STAGES) { vs = 0; vph ^= 1u; }
-        if (++ks == STAGES) { ks = 0; kph ^= 1u; }
+        __syncwarp();
+        mstamp(j, i * 3 + 1);
+        if (more) {
+          if (i == 0) { mbar_wait(k_full(ks), kph); tc_fence_after(); }
+          issue_S(i, ks, s_full(i), k_empty(ks), i == 1);      // executes after P.V_i(j) (issue order): S_i may overwrite P_i
+        }
+        mstamp(j, i * 3 + 2);
       }
+      if (++vs == STAGES) { vs = 0; vph ^= 1u; }
+      if (++ks == STAGES) { ks = 0; kph ^= 1u; }
     }
-    __syncwarp();
   } else {
     // ============================================================ softmax warpgroups (warps 2-5: query tile 0, warps 6-9: tile 1)
     const int wg = (warp - 2) >> 2;
@@ -195,9 +224,11 @@ attn_self6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const float c = a.scale_log2;
     float m_use = -INFINITY;                              // row max baked into O, l and used for P
     const int bar_mine = 1 + wg, bar_other = 2 - wg;      // named barriers 1 / 2: the exponential token
+#ifdef CID_ATTN_TOKEN
     if (wg == 1) named_bar_arrive(1, 256);                // warpgroup 0 goes first
+#endif
 #ifdef CID_ATTN_TRACE
-    const bool tr = a.trace != nullptr && blockIdx.y == 0 && blockIdx.z == 0 && (warp == 2 || warp == 6) && lane == 0 && blockIdx.x < 32;
+    const bool tr = a.trace != nullptr && blockIdx.y == 0 && blockIdx.z == 0 && (warp == 2 || warp == 6) && lane == 0 && blockIdx.x < 16;
     auto stamp = [&](int j_, int e) { if (tr && j_ < 64) a.trace[((size_t)(blockIdx.x * 2 + wg) * 64 + j_) * 8 + e] = clock64(); };
     if (tr) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); a.trace[((size_t)(blockIdx.x * 2 + wg) * 64) * 8 + 7] = smid; }
 #else
@@ -256,13 +287,17 @@ attn_self6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (need) m_use = m_new;
       const float nmc = -m_use * c;
       stamp(j, 3);
+#ifdef CID_ATTN_TOKEN
       named_bar_sync(bar_mine, 256);                      // the exponential token: the other warpgroup has finished its MUFU phase
+#endif
       stamp(j, 4);
       uint32_t pk[64];
 #pragma unroll
       for (int i = 0; i < 128; i += 2)
         pk[i >> 1] = ex2_pack<BF>(fmaf(__uint_as_float(v[i]), c, nmc), fmaf(__uint_as_float(v[i + 1]), c, nmc));
+#ifdef CID_ATTN_TOKEN
       if (!(wg == 1 && j == T - 1)) named_bar_arrive(bar_other, 256);           // (no dangling arrival after the last tile)
+#endif
       stamp(j, 5);
       // P_i(j) over the first 64 columns of this row's scores, packed pairs in key order: the A operand of P.V
 #pragma unroll

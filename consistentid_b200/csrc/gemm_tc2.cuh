@@ -25,7 +25,10 @@ namespace cid {
 // 16 epilogue warps: four per TMEM lane quarter, each draining a quarter of the tile's columns.  The epilogue of the small-K GEMMs is
 // latency-bound (ncu, profiles/r02_ncu_outproj_sd15_*: IPC 0.07 per warp - residual loads, TMEM loads, instruction fetch), not issue-bound:
 // with eight warps (two per scheduler) a 128 x 160 tile took ~14 k cycles against 1.7 k of tensor work.
-constexpr int GEMM2_EPI_WARPS = 16;
+#ifndef CID_GEMM_EPI_WARPS
+#define CID_GEMM_EPI_WARPS 16                                // (8 = the round-1 layout, kept for A/B builds: tools/build_variant.sh epi8 -DCID_GEMM_EPI_WARPS=8)
+#endif
+constexpr int GEMM2_EPI_WARPS = CID_GEMM_EPI_WARPS;
 constexpr int GEMM2_EPI_THREADS = GEMM2_EPI_WARPS * 32;
 constexpr int GEMM2_THREADS = 64 + GEMM2_EPI_THREADS;
 constexpr int GEMM2_PARTS = GEMM2_EPI_WARPS / 4;            // column ranges per lane quarter
@@ -160,42 +163,48 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     tx0 = tx * g.TW; ty0 = (rest % g.tiles_y) * g.TH; tn0 = (rest / g.tiles_y) * g.TN;
   };
 
+  // Role code is WARP-CONVERGED: all 32 lanes run the loops and poll the mbarriers, the single-thread instructions (TMA, tcgen05.mma,
+  // tcgen05.commit) sit in `if (elect_one())` blocks whose operands were computed outside, by the whole warp.  Writing the roles as
+  // `if (lane == 0) { ...loop... }` makes every TMA / MMA operand a per-thread value: the compiler then has to move it to the uniform
+  // datapath with R2UR and wraps each UTMALDG / UTCHMMA in an ELECT + BRA.U.ANY retry loop - ~90 cycles per MMA issue and ~225 per TMA
+  // issue (what round 1 measured as "the cost of a TMA instruction"); converged, the same instructions issue back to back.
   if (warp == 0) {
     // ================================================================ TMA producer
-    if (lane == 0) {
-      const uint32_t a_bytes = (g.a_mode == A_GEMM) ? uint32_t(SM::A_BYTES) : uint32_t(g.TW * g.TH * g.TN * 128);
-      int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < n_work; ++it) {
-        const GemmWork w = get_work(it);
-        const int tile = w.tile;
-        const int nt = tile % n_tiles, mt = tile / n_tiles;
-        int tn0 = 0, ty0 = 0, tx0 = 0;
-        if (g.a_mode != A_GEMM) tile_origin(mt, tn0, ty0, tx0);
-        for (int kb = w.kb0; kb < w.kb1; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sa = smem_base + stage * SM::STAGE_BYTES;
-          const uint32_t sb = sa + SM::A_BYTES;
-          mbar_expect_tx(full_bar(stage), a_bytes + uint32_t(SM::B_BYTES));
-          const int tap = kb / kb_per_tap;
-          const int cb = kb - tap * kb_per_tap;
+    const uint32_t a_bytes = (g.a_mode == A_GEMM) ? uint32_t(SM::A_BYTES) : uint32_t(g.TW * g.TH * g.TN * 128);
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0; it < n_work; ++it) {
+      const GemmWork w = get_work(it);
+      const int tile = w.tile;
+      const int nt = tile % n_tiles, mt = tile / n_tiles;
+      int tn0 = 0, ty0 = 0, tx0 = 0;
+      if (g.a_mode != A_GEMM) tile_origin(mt, tn0, ty0, tx0);
+      for (int kb = w.kb0; kb < w.kb1; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sa = smem_base + stage * SM::STAGE_BYTES;
+        const uint32_t sb = sa + SM::A_BYTES;
+        const uint32_t fb = full_bar(stage);
+        const int tap = kb / kb_per_tap;
+        const int cb = kb - tap * kb_per_tap;
+        const int ky = tap / 3, kx = tap - ky * 3;
+        if (elect_one()) {
+          mbar_expect_tx(fb, a_bytes + uint32_t(SM::B_BYTES));
           if (g.a_mode == A_GEMM) {
-            if (cb < g.kblocks_a1) tma_load_2d(sa, &tmA1, full_bar(stage), cb * GEMM_BK, mt * GEMM_BM);
-            else tma_load_2d(sa, &tmA2, full_bar(stage), (cb - g.kblocks_a1) * GEMM_BK, mt * GEMM_BM);
+            if (cb < g.kblocks_a1) tma_load_2d(sa, &tmA1, fb, cb * GEMM_BK, mt * GEMM_BM);
+            else tma_load_2d(sa, &tmA2, fb, (cb - g.kblocks_a1) * GEMM_BK, mt * GEMM_BM);
           } else if (g.a_mode == A_CONV) {
-            const int ky = tap / 3, kx = tap - ky * 3;
-            tma_load_4d(sa, &tmA1, full_bar(stage), cb * GEMM_BK, tx0 + kx - 1, ty0 + ky - 1, tn0);
+            tma_load_4d(sa, &tmA1, fb, cb * GEMM_BK, tx0 + kx - 1, ty0 + ky - 1, tn0);
           } else {
-            const int ky = tap / 3, kx = tap - ky * 3;
             const int py = (ky == 1) ? 0 : 1, dy = (ky == 0) ? -1 : 0;
             const int px = (kx == 1) ? 0 : 1, dx = (kx == 0) ? -1 : 0;
-            tma_load_5d(sa, &tmA1, full_bar(stage), cb * GEMM_BK, tx0 + dx, ty0 + dy, py * 2 + px, tn0);
+            tma_load_5d(sa, &tmA1, fb, cb * GEMM_BK, tx0 + dx, ty0 + dy, py * 2 + px, tn0);
           }
-          tma_load_2d(sb, &tmB, full_bar(stage), kb * GEMM_BK, nt * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          tma_load_2d(sb, &tmB, fb, kb * GEMM_BK, nt * BN);
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      griddep_launch_dependents();   // all loads of this CTA are in flight: the successor's prologue may overlap the remaining MMAs + epilogue
     }
+    if (elect_one()) griddep_launch_dependents();   // all loads of this CTA are in flight: the successor's prologue may overlap the remaining MMAs + epilogue
     __syncwarp();
   } else if (warp == 1) {
     // ================================================================ MMA issuer
@@ -209,21 +218,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
       mbar_wait(acc_empty(ab), aphase ^ 1u);              // epilogue has drained this accumulator (first use: free)
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + ab * ACC_STRIDE;
-      if (lane == 0) {                                     // one thread runs the whole issue loop (no per-k-block warp sync)
-        for (int kb = w.kb0; kb < w.kb1; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t a_lo = a_lo0 + uint32_t(stage) * uint32_t(SM::STAGE_BYTES / 16);
-          const uint32_t b_lo = a_lo + uint32_t(SM::A_BYTES / 16);
+      for (int kb = w.kb0; kb < w.kb1; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a_lo = a_lo0 + uint32_t(stage) * uint32_t(SM::STAGE_BYTES / 16);
+        const uint32_t b_lo = a_lo + uint32_t(SM::A_BYTES / 16);
+        const uint32_t eb = empty_bar(stage), af = acc_full(ab);
+        const uint32_t first = (kb == w.kb0) ? 0u : 1u;
+        const bool last = kb == w.kb1 - 1;
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_ss(tmem_acc, desc_make(a_lo + k * 2), desc_make(b_lo + k * 2), idesc, ((kb - w.kb0) | k) ? 1u : 0u);
-          umma_commit(empty_bar(stage));
-          if (kb == w.kb1 - 1) umma_commit(acc_full(ab));
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            umma_ss(tmem_acc, desc_make(a_lo + k * 2), desc_make(b_lo + k * 2), idesc, k ? 1u : first);
+          umma_commit(eb);
+          if (last) umma_commit(af);
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      stage = __shfl_sync(0xffffffffu, stage, 0); phase = __shfl_sync(0xffffffffu, phase, 0);
     }
   } else {
     // ================================================================ epilogue (warps 2..9)

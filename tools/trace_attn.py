@@ -34,3 +34,14 @@ for cta in list(range(0, 8)) + list(range(8, min(32, N // 128), 4)):
     period = (tt[3:, 0] - tt[2:-1, 0]).float().mean().item()
     print(f"{cta:3d} {smid:4d} | {period:8.0f} | " + " | ".join(f"{p:7.0f}" for p in ph))
 print("tile-by-tile (cta 0), cycles since tile 2 start: " + " ".join(str(int(t[0, j, 0] - t[0, 2, 0])) for j in range(2, 12)))
+
+# v6 only: the MMA thread of CTA 0 (trace rows 32 + blockIdx.x): when it saw P_i, finished issuing P.V_i, finished issuing S_i(j+1),
+# next to the softmax warpgroups' own stamps (same SM clock)
+if t[32, 3].abs().sum() > 0:
+    m, w0, w1 = t[32], t[0], t[1]
+    base = int(w0[3, 0])
+    print("CTA 0 timeline (cycles since warpgroup 0 entered tile 3); P = p_full seen, PV = P.V issued, S = S_i(j+1) issued, Sdone = softmax saw s_full")
+    for j in range(3, 7):
+        rel = lambda x: int(x) - base
+        print(f"  tile {j}: WG0 exp [{rel(w0[j, 4])}, {rel(w0[j, 5])}] arrive {rel(w0[j, 6])} | MMA P0 {rel(m[j, 0])} PV0 {rel(m[j, 1])} S0 {rel(m[j, 2])} | WG0 next Sdone {rel(w0[j + 1, 1])}"
+              f" || WG1 exp [{rel(w1[j, 4])}, {rel(w1[j, 5])}] arrive {rel(w1[j, 6])} | MMA P1 {rel(m[j, 3])} PV1 {rel(m[j, 4])} S1 {rel(m[j, 5])} | WG1 next Sdone {rel(w1[j + 1, 1])}")
