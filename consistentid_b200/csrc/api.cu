@@ -14,7 +14,8 @@
 #include "attn_cross.cuh"
 #include "attn_tc5.cuh"           // one 128-row query tile per CTA: head dims > 80 and short sequences
 #ifndef CID_ATTN_NO_V6
-#include "attn_tc6.cuh"           // two query tiles per CTA, P in tensor memory: head dims <= 80, >= 256 queries
+#include "attn_tc6.cuh"           // two query tiles per CTA, P in tensor memory (aliasing S): head dim 80, >= 256 queries
+#include "attn_tc7.cuh"           // ... with P in its own TMEM columns and S_{j+1} issued early: head dims <= 64, >= 256 queries
 #define CID_ATTN_V6 1
 #endif
 #include "elementwise.cuh"
@@ -218,9 +219,26 @@ int launch_attn_self6_t(const CUtensorMap& q, const CUtensorMap& k, const CUtens
   return 0;
 }
 #endif
+#ifdef CID_ATTN_V6
+template <int D_PAD, int BF>
+int launch_attn_self7_t(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
+  using C = Attn7Cfg<D_PAD>;
+  static bool configured[MAX_DEVICES] = {};
+  if (int rc = set_smem(attn_self7_kernel<D_PAD, BF>, C::TOTAL, "attn_self7_kernel", configured)) return rc;
+  dim3 grid((a.Nq + 255) / 256, a.H, a.B);
+  launch_pdl(attn_self7_kernel<D_PAD, BF>, dim3(grid), dim3(ATTN6_THREADS), C::TOTAL, st, q, k, v, a);
+  CID_CHECK_LAUNCH("attn_self7_kernel");
+  return 0;
+}
+#endif
 template <int D_PAD>
 int launch_attn_self(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, cudaStream_t st) {
 #ifdef CID_ATTN_V6
+#ifndef CID_ATTN_NO_V7
+  if constexpr (D_PAD <= 64) {
+    if (a.Nq >= 256) return a.is_bf16 ? launch_attn_self7_t<D_PAD, 1>(q, k, v, a, st) : launch_attn_self7_t<D_PAD, 0>(q, k, v, a, st);
+  }
+#endif
   if constexpr (D_PAD <= 80) {
     if (a.Nq >= 256) return a.is_bf16 ? launch_attn_self6_t<D_PAD, 1>(q, k, v, a, st) : launch_attn_self6_t<D_PAD, 0>(q, k, v, a, st);
   }

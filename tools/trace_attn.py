@@ -25,7 +25,7 @@ print(f"{model}: kernel {e0.elapsed_time(e1) * 1e3:.0f} us")
 t = trace.cpu().view(64, 64, 8)
 T = N // 128
 # v5: rows = CTAs (one 128-query tile each); v6: rows = (CTA, warpgroup) pairs (two tiles per CTA) and phase 3->4 is the wait for the MUFU token
-names = ["wait S", "ld S", "max", "wait Pbuf/token", "exp", "st P + arrive"]
+names = ["wait S", "ld S", "max", "exp (v7) | wait Pbuf/token (v5/v6)", "wait P.V (v7) | exp", "st P + arrive"]
 print("row smid | per-tile period | " + " | ".join(names))
 for cta in list(range(0, 8)) + list(range(8, min(32, N // 128), 4)):
     tt = t[cta, :T]
