@@ -294,7 +294,8 @@ int cid_gemm_tile_n(int N, int epi) {
 int cid_gemm(const void* A, long long lda, const void* A2, long long lda2, int K1, int K2, const void* B, void* C,
              long long ldc, int M, int N, const void* bias, const void* residual, long long ldr, const void* rowbias,
              int rows_per_group, long long ld_rowbias, int epi, void* Vt, int n_split, int heads, int hdim, int ntok,
-             float out_scale, int dtype, void* workspace, unsigned long long ws_bytes, float* chan_stats, int stats_rows, void* stream) {
+             float out_scale, int dtype, void* workspace, unsigned long long ws_bytes, float* chan_stats, int stats_rows,
+             float* row_stats, const float* ln_stats, const float* ln_colsum, float ln_eps, void* stream) {
   if (!A || !B || !C || M <= 0 || N <= 0) return fail(CID_ERR_ARG, "cid_gemm: null pointer or empty problem (M=%d N=%d)", M, N);
   if (chan_stats && (epi != CID_EPI_STORE || stats_rows <= 0 || stats_rows % 128 || M % stats_rows))
     return fail(CID_ERR_ARG, "cid_gemm: fused statistics need the plain store epilogue and stats_rows (%d) a multiple of 128 dividing M", stats_rows);
@@ -316,6 +317,10 @@ int cid_gemm(const void* A, long long lda, const void* A2, long long lda2, int K
   g.rowbias = rowbias; g.rows_per_group = rows_per_group > 0 ? rows_per_group : 1; g.ld_rowbias = ld_rowbias;
   g.epi = epi; g.is_bf16 = dtype == CID_BF16; g.Vt = Vt; g.n_split = n_split; g.heads = heads; g.hdim = hdim; g.ntok = ntok;
   g.out_scale = out_scale; g.chan_stats = chan_stats; g.stats_rows = stats_rows;
+  if (row_stats && epi != CID_EPI_STORE) return fail(CID_ERR_ARG, "cid_gemm: row_stats needs the plain store epilogue");
+  if ((ln_stats != nullptr) != (ln_colsum != nullptr)) return fail(CID_ERR_ARG, "cid_gemm: ln_stats and ln_colsum go together");
+  if (ln_stats && (reinterpret_cast<uintptr_t>(ln_stats) & 7)) return fail(CID_ERR_ARG, "cid_gemm: ln_stats must be 8-byte aligned");
+  g.row_stats = row_stats; g.ln_stats = ln_stats; g.ln_colsum = ln_colsum; g.ln_eps = ln_eps; g.ln_width = K1 + K2;
   return dispatch_gemm(bn, ta1, ta2, tb, g, (M + 127) / 128, workspace, (size_t)ws_bytes, static_cast<cudaStream_t>(stream));
 }
 

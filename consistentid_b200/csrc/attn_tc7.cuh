@@ -213,6 +213,11 @@ attn_self7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const float c = a.scale_log2;
     float m_use = -INFINITY;                              // row max baked into O, l and used for P
     float l_run = 0.f;                                    // row sum of the (unrounded) probabilities, same scaling as O
+    // The two warpgroups have identical, deterministic work: started together they stay in lock-step - both in their exponentials (sharing
+    // the MUFU), then both in the MUFU-free part of a tile (score load, row max, barrier hand-offs: ~1/4 of the period) with the MUFU idle.
+    // Half a period of head start for warpgroup 0 puts them in anti-phase, which persists: one warpgroup's MUFU-free part then overlaps the
+    // other's exponentials (phase trace, profiles/r02_attn_phase_trace_v7_*.txt).
+    if (wg == 1 && T > 2) { const long long t0 = clock64(); while (clock64() - t0 < 1400) { } }
 #ifdef CID_ATTN_TRACE
     const bool tr = a.trace != nullptr && blockIdx.y == 0 && blockIdx.z == 0 && (warp == 2 || warp == 6) && lane == 0 && blockIdx.x < 16;
     auto stamp = [&](int j_, int e) { if (tr && j_ < 64) a.trace[((size_t)(blockIdx.x * 2 + wg) * 64 + j_) * 8 + e] = clock64(); };
@@ -277,6 +282,9 @@ attn_self7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       if (need) m_use = m_new;
       const float nmc = -m_use * c;
+      // P.V_i(j-1) must have read P_i before it is overwritten below.  It was issued a whole tile ago: probe the barrier now (the probe's
+      // latency hides under the exponentials) and only fall back to a blocking wait if it really has not retired yet.
+      const bool pv_ok = (j == 0) || mbar_test(pv_done(wg), uint32_t((j - 1) & 1));
       stamp(j, 3);
       // P = 2^((s - m_use) c) in fp32, row sum in four partial sums, packed to 16 bits for the MMA
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
@@ -289,7 +297,8 @@ attn_self7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       stamp(j, 4);
-      if (j > 0) { mbar_wait(pv_done(wg), uint32_t((j - 1) & 1)); tc_fence_after(); }     // P.V_i(j-1) has read P_i (issued ~a tile ago)
+      if (!pv_ok) mbar_wait(pv_done(wg), uint32_t((j - 1) & 1));
+      tc_fence_after();
       stamp(j, 5);
 #pragma unroll
       for (int cc = 0; cc < 64; cc += 16) {

@@ -43,6 +43,17 @@ struct GemmArgs {
   // one sample (checked on the host).  NULL: off.
   float* chan_stats;
   int stats_rows;
+  // LayerNorm folded into the GEMMs on either side of it (no standalone LayerNorm pass):
+  //   producer  row_stats != NULL (EPI_STORE): per ROW sum and sum of squares of the stored values are added to row_stats[row][2] (fp32, zeroed
+  //             by the caller; the row's N columns may be spread over several tiles / warps);
+  //   consumer  ln_stats != NULL (any flavour): A holds the UN-normalised rows x, B = W . diag(gamma), bias = b + W . beta, ln_colsum[c] =
+  //             sum_k B[c, k]; the epilogue forms  LN(x) W^T + b = rstd_r (x_r . B_c - mean_r colsum_c) + bias_c  with mean / rstd of row r
+  //             from ln_stats[r] = {sum, sum of squares} over ln_width elements.
+  float* row_stats;
+  const float* ln_stats;
+  const float* ln_colsum;
+  float ln_eps;
+  int ln_width;
 };
 
 constexpr int GEMM_BM = 128;

@@ -42,7 +42,8 @@ struct Gemm2Smem {
   static constexpr int BIAS_OFF = BAR_OFF + 256;             // 2 x BN floats
   static constexpr int FLAG_OFF = BIAS_OFF + 2 * BN * 4;     // split-K "last arriver" flag
   static constexpr int STAT_OFF = FLAG_OFF + 16;             // 2 x [sum | sumsq] x BN floats: per-tile column statistics (fused GroupNorm stats)
-  static constexpr int TOTAL = STAT_OFF + 2 * 2 * BN * 4 + 1024;
+  static constexpr int CS_OFF = STAT_OFF + 2 * 2 * BN * 4;   // 2 x BN floats: column sums of the gamma-scaled weights (folded LayerNorm)
+  static constexpr int TOTAL = CS_OFF + 2 * BN * 4 + 1024;
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(GEMM2_EPI_THREADS) : "memory"); }
@@ -122,6 +123,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + SM::BAR_OFF + 8 * (2 * STAGES + 4));
   float* bias_s = reinterpret_cast<float*>(smem_gen + SM::BIAS_OFF);
   float* stat_s = reinterpret_cast<float*>(smem_gen + SM::STAT_OFF);
+  float* cs_s = reinterpret_cast<float*>(smem_gen + SM::CS_OFF);
 
   const int warp = warp_id();
   const int lane = lane_id();
@@ -288,6 +290,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
       // stage this tile's bias slice (fp32) in smem; buffer alternates with the accumulator
       float* bs = bias_s + ab * BN;
       for (int j = et; j < BN; j += GEMM2_EPI_THREADS) bs[j] = (g.bias && n0 + j < g.N) ? load16(g.bias, n0 + j, bf) : 0.f;
+      // folded LayerNorm (consumer side): v = acc * lnA + lnB * colsum[c] + bias[c] with lnA = rstd_r, lnB = -rstd_r mean_r (1, 0 when off)
+      float* cs = cs_s + ab * BN;
+      float lnA = 1.f, lnB = 0.f;
+      if (g.ln_stats != nullptr) {
+        for (int j = et; j < BN; j += GEMM2_EPI_THREADS) cs[j] = (n0 + j < g.N) ? g.ln_colsum[n0 + j] : 0.f;
+        if (row_ok) {
+          const float2 st2 = *reinterpret_cast<const float2*>(g.ln_stats + 2 * grow);
+          const float inv_w = 1.f / float(g.ln_width);
+          const float mean = st2.x * inv_w;
+          lnA = rsqrtf(fmaxf(st2.y * inv_w - mean * mean, 0.f) + g.ln_eps);
+          lnB = -lnA * mean;
+        }
+      } else {
+        for (int j = et; j < BN; j += GEMM2_EPI_THREADS) cs[j] = 0.f;
+      }
+      float rsum = 0.f, rsq = 0.f;                           // producer side: this thread's share of its row's LayerNorm statistics
       const bool do_stats = EPI == EPI_STORE && g.chan_stats != nullptr;
       float* st = stat_s + ab * 2 * BN;
       if (do_stats) for (int j = et; j < 2 * BN; j += GEMM2_EPI_THREADS) st[j] = 0.f;
@@ -391,8 +409,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
               uint32_t packed[8];
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
-                const float v0 = __uint_as_float(a[j]) + bs[ch * 16 + j], v1 = __uint_as_float(a[j + 1]) + bs[ch * 16 + j + 1];
-                const float g0 = __uint_as_float(b[j]) + bs[HALF + ch * 16 + j], g1 = __uint_as_float(b[j + 1]) + bs[HALF + ch * 16 + j + 1];
+                const float v0 = fmaf(__uint_as_float(a[j]), lnA, fmaf(lnB, cs[ch * 16 + j], bs[ch * 16 + j]));
+                const float v1 = fmaf(__uint_as_float(a[j + 1]), lnA, fmaf(lnB, cs[ch * 16 + j + 1], bs[ch * 16 + j + 1]));
+                const float g0 = fmaf(__uint_as_float(b[j]), lnA, fmaf(lnB, cs[HALF + ch * 16 + j], bs[HALF + ch * 16 + j]));
+                const float g1 = fmaf(__uint_as_float(b[j + 1]), lnA, fmaf(lnB, cs[HALF + ch * 16 + j + 1], bs[HALF + ch * 16 + j + 1]));
                 packed[j >> 1] = pack16(v0 * gelu_erf(g0), v1 * gelu_erf(g1), bf);
               }
               uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(g.C) + grow * g.ldc + out_col0 + ch * 16);
@@ -422,7 +442,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             float v[16];
             if (active) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(a[j]) + bs[ch * 16 + j];
+              for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(a[j]), lnA, fmaf(lnB, cs[ch * 16 + j], bs[ch * 16 + j]));
               if (g.rowbias) {
                 const uint16_t* rb = reinterpret_cast<const uint16_t*>(g.rowbias) + (grow / g.rows_per_group) * g.ld_rowbias + col0;
                 if (full && ((reinterpret_cast<uintptr_t>(rb) & 15) == 0)) {
@@ -465,6 +485,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
                 }
+                if (EPI == EPI_STORE && g.row_stats != nullptr) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) if (full || col0 + j < g.N) { rsum += v[j]; rsq = fmaf(v[j], v[j], rsq); }
+                }
                 uint16_t* crow = reinterpret_cast<uint16_t*>(g.C) + grow * g.ldc + col0;
                 if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
                   float lo[8], hi[8];
@@ -492,6 +516,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
               }
             }
           }
+        }
+        if (EPI == EPI_STORE && g.row_stats != nullptr && row_ok && ch_beg < ch_end) {
+          atomicAdd(g.row_stats + 2 * grow, rsum); atomicAdd(g.row_stats + 2 * grow + 1, rsq);
         }
         if (do_stats) {
           // the four row quarters of this tile were combined in smem: one global reduction per column and statistic

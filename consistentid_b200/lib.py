@@ -35,7 +35,7 @@ _SIGS = {
     "cid_last_error": ([], C.c_char_p),
     "cid_gemm_tile_n": ([_i, _i], _i),
     "cid_set_splitk": ([_i, _i], _i),
-    "cid_gemm": ([_vp, _ll, _vp, _ll, _i, _i, _vp, _vp, _ll, _i, _i, _vp, _vp, _ll, _vp, _i, _ll, _i, _vp, _i, _i, _i, _i, _f, _i, _vp, C.c_ulonglong, _vp, _i, _vp], _i),
+    "cid_gemm": ([_vp, _ll, _vp, _ll, _i, _i, _vp, _vp, _ll, _i, _i, _vp, _vp, _ll, _vp, _i, _ll, _i, _vp, _i, _i, _i, _i, _f, _i, _vp, C.c_ulonglong, _vp, _i, _vp, _vp, _vp, _f, _vp], _i),
     "cid_conv3x3": ([_vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _ll, _vp, _ll, _f, _i, _vp, C.c_ulonglong, _vp, _vp], _i),
     "cid_attn_self": ([_vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp], _i),
     "cid_attn_self_ragged": ([_vp, _ll, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp], _i),

@@ -82,10 +82,13 @@ def _chk(t, name):
 
 
 def gemm(a, w, out, bias=None, residual=None, rowbias=None, rows_per_group=1, a2=None, epi=EPI_STORE, vt=None,
-         n_split=0, heads=0, hdim=0, ntok=0, out_scale=1.0, chan_stats=None, stats_rows=0):
+         n_split=0, heads=0, hdim=0, ntok=0, out_scale=1.0, chan_stats=None, stats_rows=0, row_stats=None, ln=None):
     """out[M, :] = epi([a | a2] @ w.T + bias + rowbias[row // rows_per_group] + residual) * out_scale.
     a: [M, K1] (last-dim contiguous, row pitch a.stride(0)); w: [N, K1+K2] contiguous.
-    chan_stats: fp32 [M / stats_rows, N, 2] (zeroed by the caller) += per (sample, column) sum / sum of squares of ``out``."""
+    chan_stats: fp32 [M / stats_rows, N, 2] (zeroed by the caller) += per (sample, column) sum / sum of squares of ``out``.
+    row_stats: fp32 [M, 2] (zeroed by the caller) += per-row sum / sum of squares of ``out`` (the LayerNorm statistics of the next block).
+    ln = (stats [M, 2] fp32, colsum [N] fp32, eps): ``a`` is un-normalised, ``w`` / ``bias`` carry gamma / beta (weights.fold_layernorm): the
+    epilogue applies rstd * (acc - mean * colsum) + bias, i.e. LayerNorm(a) @ W.T + b without a LayerNorm pass."""
     _chk(a, "a")
     M, K1 = a.shape
     K2 = 0 if a2 is None else a2.shape[1]
@@ -100,7 +103,8 @@ def gemm(a, w, out, bias=None, residual=None, rowbias=None, rows_per_group=1, a2
         call("cid_gemm", _p(a), a.stride(0), _p(a2), 0 if a2 is None else a2.stride(0), K1, K2, _p(w), _p(out), out.stride(0),
              M, N, _p(bias), _p(residual), 0 if residual is None else residual.stride(0), _p(rowbias), rows_per_group,
              0 if rowbias is None else rowbias.stride(0), epi, _p(vt), n_split, heads, hdim, ntok, float(out_scale), _dt(a),
-             ws.data_ptr(), WORKSPACE_BYTES, _p(chan_stats), stats_rows, _stream())
+             ws.data_ptr(), WORKSPACE_BYTES, _p(chan_stats), stats_rows, _p(row_stats),
+             None if ln is None else ln[0].data_ptr(), None if ln is None else ln[1].data_ptr(), 0.0 if ln is None else float(ln[2]), _stream())
     return out
 
 

@@ -21,7 +21,7 @@ import torch
 from . import lib, ops
 from .arch import UNetSpec, attn_processor_names, param_shapes, walk
 from .lib import EPI_GEGLU, EPI_QKV
-from .weights import TensorIdent, fold_lora, interleave_geglu, pack_conv3x3, same_tensors
+from .weights import TensorIdent, fold_layernorm, fold_lora, interleave_geglu, pack_conv3x3, same_tensors
 
 N_TEXT_MAX, KROWS = 80, 96
 CIN_PAD = 64
@@ -38,6 +38,7 @@ class _Params:
         self.spec, self.dtype, self.device = spec, dtype, device
         self._items = {}     # name -> (offset, shape)
         self._staged = []    # (name, tensor) before arena allocation
+        self._f32 = set()    # names stored as raw fp32 bits
         self.kinds = kinds
         ushapes, ashapes = param_shapes(spec, rank)
         is_unet = "up" in kinds
@@ -92,8 +93,6 @@ class _Params:
                 put(t + ".po.w", U(t + ".proj_out.weight").reshape(C, C).contiguous()); put(t + ".po.b", U(t + ".proj_out.bias"))
                 for k in range(tf.layers):
                     b = f"{t}.transformer_blocks.{k}"
-                    for j in (1, 2, 3):
-                        put(f"{b}.ln{j}.g", U(f"{b}.norm{j}.weight")); put(f"{b}.ln{j}.b", U(f"{b}.norm{j}.bias"))
                     p1, p2 = pos_of[f"{b}.attn1.processor"], pos_of[f"{b}.attn2.processor"]
 
                     def folded(attn, pos, proj, out_name=None):
@@ -101,19 +100,24 @@ class _Params:
                         if adapter_sd is None:
                             return w
                         return fold_lora(w, A(f"{pos}.{proj}_lora.down.weight"), A(f"{pos}.{proj}_lora.up.weight"), lora_scale)
-                    put(f"{b}.a1.qkv.w", torch.cat([folded("attn1", p1, "to_q"), folded("attn1", p1, "to_k"), folded("attn1", p1, "to_v")], 0))
+                    ln = lambda j: (U(f"{b}.norm{j}.weight"), U(f"{b}.norm{j}.bias"))
+                    # norm1 / norm2 / norm3 are folded into the GEMM that consumes them (weights.fold_layernorm): gamma scales the weight
+                    # columns, beta becomes a bias, and the column sums feed the epilogue's mean correction (cid_gemm ln_stats / ln_colsum)
+                    wq, bq, cq = fold_layernorm(torch.cat([folded("attn1", p1, "to_q"), folded("attn1", p1, "to_k"), folded("attn1", p1, "to_v")], 0), None, *ln(1))
+                    put(f"{b}.a1.qkv.w", wq); put(f"{b}.a1.qkv.b", bq); self._put_f32(f"{b}.a1.qkv.cs", cq)
                     put(f"{b}.a1.o.w", folded("attn1", p1, "to_out", "to_out.0")); put(f"{b}.a1.o.b", U(f"{b}.attn1.to_out.0.bias"))
-                    put(f"{b}.a2.q.w", folded("attn2", p2, "to_q"))
+                    wq, bq, cq = fold_layernorm(folded("attn2", p2, "to_q"), None, *ln(2))
+                    put(f"{b}.a2.q.w", wq); put(f"{b}.a2.q.b", bq); self._put_f32(f"{b}.a2.q.cs", cq)
                     put(f"{b}.a2.k.w", folded("attn2", p2, "to_k")); put(f"{b}.a2.v.w", folded("attn2", p2, "to_v"))
                     if adapter_sd is not None:
                         put(f"{b}.a2.kip.w", A(f"{p2}.to_k_ip.weight")); put(f"{b}.a2.vip.w", A(f"{p2}.to_v_ip.weight"))
                     put(f"{b}.a2.o.w", folded("attn2", p2, "to_out", "to_out.0")); put(f"{b}.a2.o.b", U(f"{b}.attn2.to_out.0.bias"))
-                    w, bb = U(f"{b}.ff.net.0.proj.weight"), U(f"{b}.ff.net.0.proj.bias")
+                    w, bb, _ = fold_layernorm(U(f"{b}.ff.net.0.proj.weight"), U(f"{b}.ff.net.0.proj.bias"), *ln(3))
                     tile = lib.gemm_tile_n(w.shape[0], EPI_GEGLU)
                     if tile < 0:
                         raise ValueError(f"GEGLU width {w.shape[0]} unsupported")
                     wi, bi = interleave_geglu(w, bb, tile)
-                    put(f"{b}.ff1.w", wi); put(f"{b}.ff1.b", bi)
+                    put(f"{b}.ff1.w", wi); put(f"{b}.ff1.b", bi); self._put_f32(f"{b}.ff1.cs", wi.float().sum(dim=1))     # (column sums in the interleaved row order)
                     put(f"{b}.ff2.w", U(f"{b}.ff.net.2.weight")); put(f"{b}.ff2.b", U(f"{b}.ff.net.2.bias"))
             if has_sampler:
                 nm = f"down_blocks.{i}.downsamplers.0.conv" if kind == "down" else f"up_blocks.{i}.upsamplers.0.conv"
@@ -125,6 +129,11 @@ class _Params:
 
     def _put(self, name, t):
         self._staged.append((name, t.contiguous()))
+
+    def _put_f32(self, name, t):
+        """fp32 tensor kept bit-exact inside the 16-bit arena (two arena elements per value; one broadcast still moves everything)."""
+        self._f32.add(name)
+        self._staged.append((name, t.float().contiguous().view(self.dtype)))
 
     def _finalize(self):
         total, offs = 0, []
@@ -142,7 +151,8 @@ class _Params:
         n = 1
         for s in shape:
             n *= s
-        return self.arena[o:o + n].view(shape)
+        v = self.arena[o:o + n]
+        return v.view(torch.float32) if name in self._f32 else v.view(shape)
 
 
 class B200UNet:
@@ -384,24 +394,30 @@ class B200UNet:
         gn = buf("act", (M, C))
         self._groupnorm(x, C, None, 0, HW, P[tf.name + ".norm.g"], P[tf.name + ".norm.b"], 1e-6, False, gn)
         t = buf("tf_h", (M, C))
-        ops.gemm(gn, P[tf.name + ".pi.w"], t, bias=P[tf.name + ".pi.b"])
-        ln, qk = buf("tf_ln", (M, C)), buf("tf_qk", (M, 2 * C))
+        # LayerNorm statistics travel from the GEMM that writes the residual stream (row_stats: per-row sum / sum of squares, accumulated in its
+        # epilogue) to the GEMM that consumes LayerNorm(t) (ln=...: weights carry gamma / beta, the epilogue applies mean / rstd): no LayerNorm pass.
+        n_ln = 3 * tf.layers
+        ln_stats = buf(f"ln_stats.{n_ln}", (n_ln, M, 2), torch.float32)
+        ln_stats.zero_()
+        eps = 1e-5
+        ops.gemm(gn, P[tf.name + ".pi.w"], t, bias=P[tf.name + ".pi.b"], row_stats=ln_stats[0])
+        qk = buf("tf_qk", (M, 2 * C))
         vt, ao = buf("tf_vt", (NB * Hh, d, HW)), buf("tf_ao", (M, C))
         q, ffm = buf("tf_q", (M, C)), buf("tf_ffm", (M, 4 * C))
         for k in range(tf.layers):
             b = f"{tf.name}.transformer_blocks.{k}"
-            ops.layernorm(t, P[b + ".ln1.g"], P[b + ".ln1.b"], ln, M, C)
-            ops.gemm(ln, P[b + ".a1.qkv.w"], qk, epi=EPI_QKV, vt=vt, n_split=2 * C, heads=Hh, hdim=d, ntok=HW)
+            s1, s2, s3 = ln_stats[3 * k], ln_stats[3 * k + 1], ln_stats[3 * k + 2]
+            s_next = ln_stats[3 * k + 3] if k + 1 < tf.layers else None
+            ops.gemm(t, P[b + ".a1.qkv.w"], qk, bias=P[b + ".a1.qkv.b"], epi=EPI_QKV, vt=vt, n_split=2 * C, heads=Hh, hdim=d, ntok=HW,
+                     ln=(s1, P[b + ".a1.qkv.cs"], eps))
             ops.attn_self(qk[:, :C], qk[:, C:], vt, ao, NB, Hh, HW, d)
-            ops.gemm(ao, P[b + ".a1.o.w"], t, bias=P[b + ".a1.o.b"], residual=t)
-            ops.layernorm(t, P[b + ".ln2.g"], P[b + ".ln2.b"], ln, M, C)
-            ops.gemm(ln, P[b + ".a2.q.w"], q)
+            ops.gemm(ao, P[b + ".a1.o.w"], t, bias=P[b + ".a1.o.b"], residual=t, row_stats=s2)
+            ops.gemm(t, P[b + ".a2.q.w"], q, bias=P[b + ".a2.q.b"], ln=(s2, P[b + ".a2.q.cs"], eps))
             k_cat, vt_cat, n_text, n_ip = kv[b]
             ops.attn_cross(q, k_cat, vt_cat, ao, NB, Hh, HW, d, n_text, n_ip, self.ip_scale)
-            ops.gemm(ao, P[b + ".a2.o.w"], t, bias=P[b + ".a2.o.b"], residual=t)
-            ops.layernorm(t, P[b + ".ln3.g"], P[b + ".ln3.b"], ln, M, C)
-            ops.gemm(ln, P[b + ".ff1.w"], ffm, bias=P[b + ".ff1.b"], epi=EPI_GEGLU)
-            ops.gemm(ffm, P[b + ".ff2.w"], t, bias=P[b + ".ff2.b"], residual=t)
+            ops.gemm(ao, P[b + ".a2.o.w"], t, bias=P[b + ".a2.o.b"], residual=t, row_stats=s3)
+            ops.gemm(t, P[b + ".ff1.w"], ffm, bias=P[b + ".ff1.b"], epi=EPI_GEGLU, ln=(s3, P[b + ".ff1.cs"], eps))
+            ops.gemm(ffm, P[b + ".ff2.w"], t, bias=P[b + ".ff2.b"], residual=t, row_stats=s_next)
         out = buf(out_name, (M, C))
         st = self._stats_slot(out, HW, C)
         ops.gemm(t, P[tf.name + ".po.w"], out, bias=P[tf.name + ".po.b"], residual=x, chan_stats=st, stats_rows=HW if st is not None else 0)

@@ -35,6 +35,18 @@ def pack_conv3x3(w: torch.Tensor, cin_pad: int | None = None) -> torch.Tensor:
     return out.reshape(cout, 9 * cp).contiguous()
 
 
+def fold_layernorm(w, bias, gamma, beta):
+    """LayerNorm(x; gamma, beta) @ w.T + bias  ==  xhat @ (w * gamma).T + (bias + w @ beta)   with xhat = (x - mean) / std.
+    Returns (w' in w's 16-bit dtype, bias' in that dtype, colsum fp32 [N]) for the GEMM's folded-LayerNorm epilogue
+    (cid_gemm ln_stats / ln_colsum): colsum is taken over the ROUNDED w' so that mean * colsum cancels the mean part of x @ w'.T exactly."""
+    w32 = w.float() * gamma.float()[None, :]
+    b32 = w.float() @ beta.float()
+    if bias is not None:
+        b32 = b32 + bias.float()
+    wq = w32.to(w.dtype)
+    return wq.contiguous(), b32.to(w.dtype).contiguous(), wq.float().sum(dim=1).contiguous()
+
+
 class TensorIdent:
     """Identity of a tensor's CONTENT, for host-side caches keyed on "the same prompt / weight tensor as last time".
 

@@ -48,12 +48,18 @@ int cid_gemm_tile_n(int N, int epi);
  *   chan_stats  : non-NULL (plain store epilogue only) = GroupNorm statistics of the OUTPUT fused into the epilogue: per (sample, column)
  *                 sum and sum of squares are ADDED to chan_stats[(row / stats_rows) * N + col][2] (fp32, zeroed by the caller); stats_rows =
  *                 rows per sample, a multiple of 128.  Consumed by cid_gn_apply_ch: the standalone statistics pass (one re-read of the
- *                 tensor per GroupNorm) disappears. */
+ *                 tensor per GroupNorm) disappears.
+ *   LayerNorm folded into the GEMMs around it (BasicTransformerBlock norm1/2/3: no standalone LayerNorm pass):
+ *   row_stats   : non-NULL (plain store epilogue only) = the PRODUCER side: per-row sum and sum of squares of the stored row are ADDED to
+ *                 row_stats[row][2] (fp32, zeroed by the caller);
+ *   ln_stats    : non-NULL = the CONSUMER side: A holds the un-normalised rows, B = W . diag(gamma) (16-bit), bias = b + W . beta and
+ *                 ln_colsum[c] = sum_k B[c,k] (fp32, of the ROUNDED B); the epilogue forms rstd_r (A_r . B_c - mean_r colsum_c) + bias_c with
+ *                 mean / rstd of row r from ln_stats[r] over K1 + K2 elements and ln_eps - exactly LayerNorm(A) W^T + b in fp32. */
 int cid_gemm(const void* A, long long lda, const void* A2, long long lda2, int K1, int K2, const void* B,
              void* C, long long ldc, int M, int N, const void* bias, const void* residual, long long ldr,
              const void* rowbias, int rows_per_group, long long ld_rowbias, int epi, void* Vt, int n_split, int heads,
              int hdim, int ntok, float out_scale, int dtype, void* workspace, unsigned long long ws_bytes, float* chan_stats,
-             int stats_rows, void* stream);
+             int stats_rows, float* row_stats, const float* ln_stats, const float* ln_colsum, float ln_eps, void* stream);
 
 /* 3x3 convolution, padding 1, as implicit GEMM over NHWC.  X: [NB,H,W,Cin] (stride 1) or the phase-split copy
  * [NB,4,H,W,Cin] of a [NB,2H,2W,Cin] tensor (stride2 = 1; H,W are OUTPUT dims).  Wt: [Cout, 9*Cin] = (ky,kx,c) order.

@@ -28,6 +28,12 @@ def build_ref_unet(cfg: UNetConfig, seed=1234, rank=128, dtype=torch.float32):
             a = attn_by_name[name]
             p.to_k_ip.weight.data.copy_(a.to_k.weight.data + 0.02 * torch.randn(a.to_k.weight.shape, generator=g))
             p.to_v_ip.weight.data.copy_(a.to_v.weight.data + 0.02 * torch.randn(a.to_v.weight.shape, generator=g))
+    # torch's default affine init (weight 1, bias 0) would hide every gamma / beta path (the engine folds LayerNorm into the neighbouring GEMMs and
+    # GroupNorm into a per-channel affine): perturb them
+    for m in unet.modules():
+        if isinstance(m, (torch.nn.LayerNorm, torch.nn.GroupNorm)) and m.weight is not None:
+            m.weight.data.add_(0.1 * torch.randn(m.weight.shape, generator=g))
+            m.bias.data.add_(0.1 * torch.randn(m.bias.shape, generator=g))
     unet = unet.to(dtype).eval()
     for p in procs.values():
         p.to(dtype)

@@ -29,10 +29,16 @@ def _add_chan_stats(chan_stats, y, rows_per_sample):
 
 
 def gemm(a, w, out, bias=None, residual=None, rowbias=None, rows_per_group=1, a2=None, epi=0, vt=None, n_split=0, heads=0, hdim=0, ntok=0,
-         out_scale=1.0, chan_stats=None, stats_rows=0):
+         out_scale=1.0, chan_stats=None, stats_rows=0, row_stats=None, ln=None):
     x = a.float() if a2 is None else torch.cat([a.float(), a2.float()], dim=1)
     y = x @ w.float().T
     M, N = y.shape
+    if ln is not None:            # folded LayerNorm: rstd * (acc - mean * colsum), then the bias (which carries W . beta)
+        st, cs, eps = ln
+        K = x.shape[1]
+        mean = st[:, 0] / K
+        rstd = torch.rsqrt((st[:, 1] / K - mean * mean).clamp_min(0) + eps)
+        y = rstd[:, None] * (y - mean[:, None] * cs.float()[None, :])
     if bias is not None:
         y = y + bias.float()
     if rowbias is not None:
@@ -54,6 +60,8 @@ def gemm(a, w, out, bias=None, residual=None, rowbias=None, rows_per_group=1, a2
         y = F.gelu(y)
     out.copy_(y)
     _add_chan_stats(chan_stats, y, stats_rows)
+    if row_stats is not None:
+        row_stats.add_(torch.stack([y.sum(1), (y * y).sum(1)], dim=1))
     return out
 
 

@@ -230,6 +230,43 @@ def check_gemm_stats_concat(NB=2, HW=256, C1=640, C2=320, K=320, dtype=torch.bfl
     return _report(f"gemm+conv stats -> gn_apply_ch concat {C1}+{C2}", y, ref, 1.6e-2)
 
 
+def check_gemm_layernorm_fold(M=512, C=320, N=960, dtype=torch.float16, seed=0, epi="store"):
+    """LayerNorm folded into the GEMMs around it: producer GEMM (+ residual) accumulates per-row statistics in its epilogue (row_stats), the
+    consumer GEMM takes gamma-scaled weights + column sums and applies mean / rstd in ITS epilogue (ln=...).  Reference: torch LayerNorm of the
+    producer's stored 16-bit output, then the plain linear (+ GEGLU)."""
+    from consistentid_b200 import lib
+    from consistentid_b200.lib import EPI_GEGLU
+    from consistentid_b200.weights import fold_layernorm, interleave_geglu
+    ops = _ops()
+    a, w0, b0 = _rand((M, C), dtype, seed), _rand((C, C), dtype, seed + 1, C ** -0.5), _rand((C,), dtype, seed + 2)
+    res = _rand((M, C), dtype, seed + 3, 2.0) + 0.5                    # non-zero row means: the mean-correction term matters
+    t = torch.empty((M, C), dtype=dtype, device=DEV)
+    stats = torch.zeros((M, 2), dtype=torch.float32, device=DEV)
+    ops.gemm(a, w0, t, bias=b0, residual=res, row_stats=stats)
+    gamma, beta = 1 + _rand((C,), dtype, seed + 4, 0.2), _rand((C,), dtype, seed + 5, 0.2)
+    w1, b1 = _rand((N, C), dtype, seed + 6, C ** -0.5), _rand((N,), dtype, seed + 7)
+    wf, bf, cs = fold_layernorm(w1, b1, gamma, beta)
+    xn = F.layer_norm(t.float(), (C,), gamma.float(), beta.float(), 1e-5)
+    if epi == "geglu":
+        tile = lib.gemm_tile_n(N, EPI_GEGLU)
+        wi, bi = interleave_geglu(wf, bf, tile)
+        out = torch.empty((M, N // 2), dtype=dtype, device=DEV)
+        ops.gemm(t, wi, out, bias=bi, epi=EPI_GEGLU, ln=(stats, wi.float().sum(1).contiguous(), 1e-5))
+        y = xn @ w1.float().t() + b1.float()
+        ref = y[:, :N // 2] * F.gelu(y[:, N // 2:])
+    else:
+        out = torch.empty((M, N), dtype=dtype, device=DEV)
+        ops.gemm(t, wf, out, bias=bf, ln=(stats, cs, 1e-5))
+        ref = xn @ w1.float().t() + b1.float()
+    torch.cuda.synchronize()
+    tf = t.float()
+    want_stats = torch.stack([tf.sum(1), (tf * tf).sum(1)], 1)
+    r0 = _report("row_stats", stats, want_stats, 2e-3)
+    r = _report(f"gemm_ln_fold {epi} {M}x{N}x{C}", out, ref, 1.2e-2)
+    r["ok"] = r["ok"] and r0["ok"]; r["stats_max_err"] = r0["max_err"]
+    return r
+
+
 def check_attn_cross(B=2, H=2, N=256, d=64, dtype=torch.float16, n_text=77, n_ip=4, ip_scale=1.0, seed=0):
     ops = _ops()
     C = H * d
@@ -508,6 +545,9 @@ CHECKS = {
     "conv_stats_w128": (check_conv_stats, dict(NB=1, H=4, W=128, Cin=64, Cout=160)),
     "conv_stats_split": (check_conv_stats, dict(NB=16, H=16, W=16, Cin=640, Cout=1280)),
     "gemm_stats_concat": (check_gemm_stats_concat, {}),
+    "gemm_ln_fold": (check_gemm_layernorm_fold, dict(M=512, C=320, N=960)),
+    "gemm_ln_fold_1280": (check_gemm_layernorm_fold, dict(M=384, C=1280, N=1280, dtype=B16)),
+    "gemm_ln_fold_geglu": (check_gemm_layernorm_fold, dict(M=256, C=640, N=5120, epi="geglu")),
     "gn_320": (check_groupnorm, dict(C1=320)),
     "gn_concat": (check_groupnorm, dict(C1=640, C2=320, HW=1024)),
     "gn_2560": (check_groupnorm, dict(C1=1280, C2=1280, HW=64, NB=3, dtype=B16)),
