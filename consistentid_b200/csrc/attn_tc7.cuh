@@ -213,11 +213,8 @@ attn_self7_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const float c = a.scale_log2;
     float m_use = -INFINITY;                              // row max baked into O, l and used for P
     float l_run = 0.f;                                    // row sum of the (unrounded) probabilities, same scaling as O
-    // The two warpgroups have identical, deterministic work: started together they stay in lock-step - both in their exponentials (sharing
-    // the MUFU), then both in the MUFU-free part of a tile (score load, row max, barrier hand-offs: ~1/4 of the period) with the MUFU idle.
-    // Half a period of head start for warpgroup 0 puts them in anti-phase, which persists: one warpgroup's MUFU-free part then overlaps the
-    // other's exponentials (phase trace, profiles/r02_attn_phase_trace_v7_*.txt).
-    if (wg == 1 && T > 2) { const long long t0 = clock64(); while (clock64() - t0 < 1400) { } }
+    // (Measured and dropped: half a period of head start for one warpgroup, to put the two in anti-phase - the exponential phase is ~70 % of
+    // a tile, so the warpgroups overlap in it whatever the offset; no change in kernel time, profiles/r02_attn_phase_trace_v7b_sd15.txt.)
 #ifdef CID_ATTN_TRACE
     const bool tr = a.trace != nullptr && blockIdx.y == 0 && blockIdx.z == 0 && (warp == 2 || warp == 6) && lane == 0 && blockIdx.x < 16;
     auto stamp = [&](int j_, int e) { if (tr && j_ < 64) a.trace[((size_t)(blockIdx.x * 2 + wg) * 64 + j_) * 8 + e] = clock64(); };
