@@ -140,7 +140,7 @@ class _Params:
         for name, t in self._staged:
             offs.append(total)
             total += (t.numel() + 127) // 128 * 128        # 256-byte aligned slots
-        self.arena = torch.empty(total, dtype=self.dtype, device=self.device)
+        self.arena = torch.zeros(total, dtype=self.dtype, device=self.device)      # (zeros: the alignment padding between slots is part of the broadcast / checksums)
         for (name, t), o in zip(self._staged, offs):
             self.arena[o:o + t.numel()].copy_(t.reshape(-1))
             self._items[name] = (o, tuple(t.shape))

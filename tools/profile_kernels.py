@@ -21,6 +21,12 @@ def cases(model):
     x = rnd((M, C), dt); res = rnd((M, C), dt); o = torch.empty((M, C), dtype=dt, device="cuda")
     w = rnd((C, C), dt, C ** -0.5); b = rnd((C,), dt)
     out["gemm_out_proj"] = (lambda: ops.gemm(x, w, o, bias=b, residual=res), 2.0 * M * C * C)
+    if model == "sdxl":     # the level-2 workhorse: 8192 x 1280 x 1280, residual stream updated in place, LayerNorm row statistics in the epilogue
+        M2, C2 = 8192, 1280
+        x2 = rnd((M2, C2), dt); t2 = rnd((M2, C2), dt); w2_ = rnd((C2, C2), dt, C2 ** -0.5); b2 = rnd((C2,), dt)
+        rs2 = torch.zeros((M2, 2), dtype=torch.float32, device="cuda")
+        out["gemm_out_proj_1280"] = (lambda: ops.gemm(x2, w2_, t2, bias=b2, residual=t2, row_stats=rs2), 2.0 * M2 * C2 * C2)
+        out["gemm_plain_1280"] = (lambda: ops.gemm(x2, w2_, t2, bias=b2), 2.0 * M2 * C2 * C2)
     wqkv = rnd((3 * C, C), dt, C ** -0.5); qk = torch.empty((M, 2 * C), dtype=dt, device="cuda"); vt = torch.empty((NB * heads, d, H * W), dtype=dt, device="cuda")
     out["gemm_qkv"] = (lambda: ops.gemm(x, wqkv, qk, epi=lib.EPI_QKV, vt=vt, n_split=2 * C, heads=heads, hdim=d, ntok=H * W), 2.0 * M * 3 * C * C)
     w1 = rnd((8 * C, C), dt, C ** -0.5); b1 = rnd((8 * C,), dt)
@@ -37,6 +43,8 @@ def cases(model):
     return out
 
 if __name__ == "__main__":
+    if os.environ.get("CID_TOOL_SPLITK"):          # tail-balancing policy override for experiments: "max_split,min_kblocks"
+        lib.set_splitk(*[int(v) for v in os.environ["CID_TOOL_SPLITK"].split(",")])
     model = sys.argv[1] if len(sys.argv) > 1 else "sd15"
     sel = sys.argv[2:]
     res = {}

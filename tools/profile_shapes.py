@@ -12,6 +12,8 @@ from consistentid_b200.pipeline import B200Denoiser
 from consistentid_b200.scheduler import B200Scheduler
 from consistentid_b200.unet import B200UNet
 
+if os.environ.get("CID_TOOL_SPLITK"):          # tail-balancing policy override for experiments: "max_split,min_kblocks"
+    lib.set_splitk(*[int(v) for v in os.environ["CID_TOOL_SPLITK"].split(",")])
 wl_name = sys.argv[1] if len(sys.argv) > 1 else "sd15"
 wl = bench.WORKLOADS[wl_name]
 dtype = torch.float16 if wl["dtype"] == "fp16" else torch.bfloat16
