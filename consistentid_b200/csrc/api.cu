@@ -62,7 +62,7 @@ void resolve_encode() {
 
 // rank-R tiled map over 16-bit elements, 128B swizzle; dims[0] is the contiguous dimension.
 int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-             const cuuint32_t* box) {
+             const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   std::call_once(g_encode_once, resolve_encode);
   if (!g_encode) return fail(CID_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -70,7 +70,7 @@ int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
   for (int i = 0; i + 1 < rank; ++i)
     if (strides_bytes[i] % 16 != 0) return fail(CID_ERR_ARG, "TMA stride[%d]=%llu not a multiple of 16 bytes", i, (unsigned long long)strides_bytes[i]);
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CID_ERR_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", int(r), rank);
   return 0;
@@ -80,6 +80,14 @@ int map_2d(CUtensorMap* m, const void* base, long long inner, long long rows, lo
   cuuint64_t str[1] = {cuuint64_t(pitch_elems) * 2};
   cuuint32_t box[2] = {64, cuuint32_t(box_rows)};
   return make_map(m, base, 2, dims, str, box);
+}
+
+// output map of the TMA-store epilogue: [rows, N] 16-bit, boxes of 32 columns (64 B) x 128 rows, 64B swizzle (gemm_tc2.cuh staging layout)
+int map_out(CUtensorMap* m, const void* base, long long cols, long long rows, long long pitch_elems) {
+  cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  cuuint64_t str[1] = {cuuint64_t(pitch_elems) * 2};
+  cuuint32_t box[2] = {32, 128};
+  return make_map(m, base, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: remember it per (kernel, device) so that one
@@ -117,13 +125,26 @@ int num_sms() {
 // (K >= 3072) per unit, at most 4 units.  cid_set_splitk overrides (tests force it on to exercise the path).
 constexpr size_t WS_COUNTER_BYTES = 4096;
 int g_splitk_min_kb = 48, g_splitk_max = 4;
+#ifdef CID_NO_TMA_EPILOGUE
+bool g_tma_epilogue = false;      // A/B builds: register epilogue everywhere
+#else
+bool g_tma_epilogue = true;
+#endif
 
 template <int BN, int STAGES, int EPI, int BF>
-int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, void* ws, size_t ws_bytes,
-                 cudaStream_t st) {
-  using SM = Gemm2Smem<BN, STAGES>;
+int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& c, const GemmArgs& g, int grid,
+                 const GemmSched& sched, int n_tiles, cudaStream_t st) {
+  using SM = Gemm2Smem<BN, STAGES, EPI == EPI_STORE_TMA>;
   static bool configured[MAX_DEVICES] = {};
   if (int rc = set_smem(gemm_tc2_kernel<BN, STAGES, EPI, BF>, SM::TOTAL, "gemm_tc2_kernel", configured)) return rc;
+  launch_pdl(gemm_tc2_kernel<BN, STAGES, EPI, BF>, dim3(grid), dim3(GEMM2_THREADS), SM::TOTAL, st, a1, a2, b, c, g, n_tiles, sched);
+  CID_CHECK_LAUNCH("gemm_tc2_kernel");
+  return 0;
+}
+// STAGES_T: ring depth of the TMA-store flavour (its 128 x BN staging tile comes out of the operand ring's shared memory)
+template <int BN, int STAGES, int STAGES_T>
+int launch_gemm2_any(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap* c_out, const GemmArgs& g, int m_tiles,
+                     void* ws, size_t ws_bytes, cudaStream_t st) {
   const int n_tiles = (g.N + BN - 1) / BN;
   const int total = n_tiles * m_tiles;
   const int G = num_sms();
@@ -146,33 +167,28 @@ int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap
       if (sched.tail_tiles * sp > grid) grid = sched.tail_tiles * sp;
     }
   }
-  launch_pdl(gemm_tc2_kernel<BN, STAGES, EPI, BF>, dim3(grid), dim3(GEMM2_THREADS), SM::TOTAL, st, a1, a2, b, g, n_tiles, sched);
-  CID_CHECK_LAUNCH("gemm_tc2_kernel");
-  return 0;
-}
-template <int BN, int STAGES>
-int launch_gemm2_any(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, void* ws, size_t ws_bytes,
-                     cudaStream_t st) {
   const int flavour = g.epi == EPI_GEGLU ? EPI_GEGLU : (g.epi == EPI_QKV ? EPI_QKV : EPI_STORE);      // EPI_GELU rides on the store flavour
-#define CID_G2(E) (g.is_bf16 ? launch_gemm2<BN, STAGES, E, 1>(a1, a2, b, g, m_tiles, ws, ws_bytes, st) \
-                             : launch_gemm2<BN, STAGES, E, 0>(a1, a2, b, g, m_tiles, ws, ws_bytes, st))
+#define CID_G2(S, E) (g.is_bf16 ? launch_gemm2<BN, S, E, 1>(a1, a2, b, c_out ? *c_out : b, g, grid, sched, n_tiles, st) \
+                                : launch_gemm2<BN, S, E, 0>(a1, a2, b, c_out ? *c_out : b, g, grid, sched, n_tiles, st))
   if constexpr (BN >= 32) {
-    if (flavour == EPI_GEGLU) return CID_G2(EPI_GEGLU);
-    if (flavour == EPI_QKV) return CID_G2(EPI_QKV);
+    if (flavour == EPI_GEGLU) return CID_G2(STAGES, EPI_GEGLU);
+    if (flavour == EPI_QKV) return CID_G2(STAGES, EPI_QKV);
+    // store epilogue through shared memory + TMA whenever the caller could build an output map and no tail tile is split
+    if (c_out != nullptr && sched.ksplit == 1 && g_tma_epilogue) return CID_G2(STAGES_T, EPI_STORE_TMA);
   } else {
     if (flavour != EPI_STORE) return fail(CID_ERR_UNSUPPORTED, "GEGLU / QKV epilogues need an N tile >= 32");
   }
-  return CID_G2(EPI_STORE);
+  return CID_G2(STAGES, EPI_STORE);
 #undef CID_G2
 }
 
-int dispatch_gemm(int bn, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g, int m_tiles, void* ws,
-                  size_t ws_bytes, cudaStream_t st) {
+int dispatch_gemm(int bn, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap* c_out, const GemmArgs& g,
+                  int m_tiles, void* ws, size_t ws_bytes, cudaStream_t st) {
   switch (bn) {
-    case 256: return launch_gemm2_any<256, 4>(a1, a2, b, g, m_tiles, ws, ws_bytes, st);
-    case 160: return launch_gemm2_any<160, 5>(a1, a2, b, g, m_tiles, ws, ws_bytes, st);
-    case 64: return launch_gemm2_any<64, 8>(a1, a2, b, g, m_tiles, ws, ws_bytes, st);
-    case 16: return launch_gemm2_any<16, 8>(a1, a2, b, g, m_tiles, ws, ws_bytes, st);
+    case 256: return launch_gemm2_any<256, 4, 3>(a1, a2, b, c_out, g, m_tiles, ws, ws_bytes, st);
+    case 160: return launch_gemm2_any<160, 5, 4>(a1, a2, b, c_out, g, m_tiles, ws, ws_bytes, st);
+    case 64: return launch_gemm2_any<64, 8, 6>(a1, a2, b, c_out, g, m_tiles, ws, ws_bytes, st);
+    case 16: return launch_gemm2_any<16, 8, 8>(a1, a2, b, nullptr, g, m_tiles, ws, ws_bytes, st);
   }
   return fail(CID_ERR_UNSUPPORTED, "no GEMM instantiation for tile N %d", bn);
 }
@@ -321,7 +337,14 @@ int cid_gemm(const void* A, long long lda, const void* A2, long long lda2, int K
   if ((ln_stats != nullptr) != (ln_colsum != nullptr)) return fail(CID_ERR_ARG, "cid_gemm: ln_stats and ln_colsum go together");
   if (ln_stats && (reinterpret_cast<uintptr_t>(ln_stats) & 7)) return fail(CID_ERR_ARG, "cid_gemm: ln_stats must be 8-byte aligned");
   g.row_stats = row_stats; g.ln_stats = ln_stats; g.ln_colsum = ln_colsum; g.ln_eps = ln_eps; g.ln_width = K1 + K2;
-  return dispatch_gemm(bn, ta1, ta2, tb, g, (M + 127) / 128, workspace, (size_t)ws_bytes, static_cast<cudaStream_t>(stream));
+  // TMA-store epilogue (plain / GELU store flavours): 16-byte aligned rows of C and of the residual; rowbias constant inside a 128-row tile
+  CUtensorMap tc; const CUtensorMap* pc = nullptr;
+  if ((epi == CID_EPI_STORE || epi == CID_EPI_GELU) && bn >= 64 && N % 8 == 0 && ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+      (!residual || (ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0))) {
+    if ((rc = map_out(&tc, C, N, M, ldc))) return rc;
+    pc = &tc;
+  }
+  return dispatch_gemm(bn, ta1, ta2, tb, pc, g, (M + 127) / 128, workspace, (size_t)ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int cid_conv3x3(const void* X, const void* Wt, void* Y, long long ldy, int NB, int H, int W, int Cin, int Cout, int stride2,
@@ -365,7 +388,15 @@ int cid_conv3x3(const void* X, const void* Wt, void* Y, long long ldy, int NB, i
     if (g.TN != 1) return fail(CID_ERR_UNSUPPORTED, "cid_conv3x3: fused statistics need every 128-pixel tile inside one sample (H*W = %d too small)", H * W);
     g.chan_stats = chan_stats; g.stats_rows = H * W;
   }
-  return dispatch_gemm(bn, ta, ta, tb, g, m_tiles, workspace, (size_t)ws_bytes, static_cast<cudaStream_t>(stream));
+  // TMA-store epilogue: the 128 pixels of a tile must be 128 CONSECUTIVE rows of Y (full-width row blocks, or 128-pixel strips of wide rows)
+  CUtensorMap tc; const CUtensorMap* pc = nullptr;
+  const bool rows_contiguous = (g.TW == W && g.TW * g.TH * g.TN == 128 && (H % g.TH) == 0 && (g.TN == 1 || NB % g.TN == 0)) || (W % 128 == 0 && g.TW == 128);
+  if (rows_contiguous && bn >= 64 && Cout % 8 == 0 && ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0 &&
+      (!residual || (ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0))) {
+    if ((rc = map_out(&tc, Y, Cout, (long long)NB * H * W, ldy))) return rc;
+    pc = &tc;
+  }
+  return dispatch_gemm(bn, ta, ta, tb, pc, g, m_tiles, workspace, (size_t)ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 static int attn_self_impl(const void* Q, long long q_pitch, const void* K, long long k_pitch, const void* Vt, void* O, long long ldo,

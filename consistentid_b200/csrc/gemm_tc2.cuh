@@ -33,7 +33,7 @@ constexpr int GEMM2_EPI_THREADS = GEMM2_EPI_WARPS * 32;
 constexpr int GEMM2_THREADS = 64 + GEMM2_EPI_THREADS;
 constexpr int GEMM2_PARTS = GEMM2_EPI_WARPS / 4;            // column ranges per lane quarter
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool TMA_OUT = false>
 struct Gemm2Smem {
   static constexpr int A_BYTES = GEMM_BM * 128;
   static constexpr int B_BYTES = BN * 128;
@@ -43,7 +43,10 @@ struct Gemm2Smem {
   static constexpr int FLAG_OFF = BIAS_OFF + 2 * BN * 4;     // split-K "last arriver" flag
   static constexpr int STAT_OFF = FLAG_OFF + 16;             // 2 x [sum | sumsq] x BN floats: per-tile column statistics (fused GroupNorm stats)
   static constexpr int CS_OFF = STAT_OFF + 2 * 2 * BN * 4;   // 2 x BN floats: column sums of the gamma-scaled weights (folded LayerNorm)
-  static constexpr int TOTAL = CS_OFF + 2 * BN * 4 + 1024;
+  // TMA-store flavour: the 128 x BN 16-bit output tile (and, before it, the residual tile) staged as BN/32 boxes of [128 rows x 64 B], 64B-swizzled
+  static constexpr int OUT_OFF = (CS_OFF + 2 * BN * 4 + 1023) / 1024 * 1024;
+  static constexpr int OUT_BYTES = TMA_OUT ? GEMM_BM * BN * 2 : 0;
+  static constexpr int TOTAL = OUT_OFF + OUT_BYTES + 1024;
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(GEMM2_EPI_THREADS) : "memory"); }
@@ -108,10 +111,13 @@ struct GemmWork { int tile, kb0, kb1, split, tail_idx; };
 template <int BN, int STAGES, int EPI, int BF>
 __global__ void __launch_bounds__(GEMM2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-                const __grid_constant__ CUtensorMap tmB, const GemmArgs g, const int n_tiles, const GemmSched sched) {
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const GemmArgs g, const int n_tiles,
+                const GemmSched sched) {
+  constexpr bool TMAO = EPI == EPI_STORE_TMA;                  // store flavour with the output (and residual) tile staged through shared memory
+  constexpr bool STOREF = EPI == EPI_STORE || TMAO;
   static_assert(BN % 32 == 0 || BN == 16, "column split");
   constexpr int ACC_STRIDE = 256;                              // TMEM column offset between the two accumulators
-  using SM = Gemm2Smem<BN, STAGES>;
+  using SM = Gemm2Smem<BN, STAGES, TMAO>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -277,6 +283,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
       return ((long long)tn0 * g.H + ty0) * g.W + tx0;
     };
     volatile int* last_flag = reinterpret_cast<volatile int*>(smem_gen + SM::FLAG_OFF);
+    // TMA-store flavour: staging tile + the coalesced residual loader (chunk q of the tile = row q / (BN/8), 16-byte column chunk q % (BN/8))
+    uint8_t* stage_out = smem_gen + SM::OUT_OFF;
+    constexpr int NPF = TMAO ? (GEMM_BM * BN / 8) / GEMM2_EPI_THREADS : 1;
+    static_assert(!TMAO || (GEMM_BM * BN / 8) % GEMM2_EPI_THREADS == 0, "tile chunks must divide over the epilogue threads");
+    uint4 rpf[NPF];
+    auto load_res_tile = [&](int tile_, uint4 (&dst)[NPF]) {
+      const long long r0 = my_row_base(tile_);
+      const int c0 = (tile_ % n_tiles) * BN;
+#pragma unroll
+      for (int i = 0; i < NPF; ++i) {
+        const int q = et + i * GEMM2_EPI_THREADS, rr = q / (BN / 8), c16 = q - rr * (BN / 8);
+        const long long gr = r0 + rr;
+        const int gc = c0 + c16 * 8;
+        dst[i] = (gr < g.M && gc + 8 <= g.N) ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(g.residual) + gr * g.ldr + gc))
+                                             : make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
     for (int it = 0; it < n_work; ++it) {
       const GemmWork w = get_work(it);
       const int tile = w.tile;
@@ -306,24 +329,45 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         for (int j = et; j < BN; j += GEMM2_EPI_THREADS) cs[j] = 0.f;
       }
       float rsum = 0.f, rsq = 0.f;                           // producer side: this thread's share of its row's LayerNorm statistics
-      const bool do_stats = EPI == EPI_STORE && g.chan_stats != nullptr;
+      const bool do_stats = STOREF && g.chan_stats != nullptr;
       float* st = stat_s + ab * 2 * BN;
       if (do_stats) for (int j = et; j < 2 * BN; j += GEMM2_EPI_THREADS) st[j] = 0.f;
       // prefetch residual rows for this thread's chunks (latency overlaps the wait for the accumulator; prefetching a whole
       // tile ahead was measured: no gain at BN=160, register spills at BN=256)
-      uint4 res[MAXCH][2];
+      constexpr int RES_REGS = TMAO ? 1 : MAXCH;
+      uint4 res[RES_REGS][2];
       const bool use_res = g.residual != nullptr && !geglu && row_ok;
       const uint16_t* rrow = use_res ? reinterpret_cast<const uint16_t*>(g.residual) + grow * g.ldr + n0 : nullptr;
       const bool res_vec = use_res && ((reinterpret_cast<uintptr_t>(rrow) & 15) == 0) && (n0 + BN <= g.N);
+      if constexpr (!TMAO) {
 #pragma unroll
-      for (int c = 0; c < MAXCH; ++c) {
-        const int ch = ch_beg + c;
-        if (res_vec && ch < ch_end) {
-          res[c][0] = reinterpret_cast<const uint4*>(rrow + ch * 16)[0];
-          res[c][1] = reinterpret_cast<const uint4*>(rrow + ch * 16)[1];
+        for (int c = 0; c < MAXCH; ++c) {
+          const int ch = ch_beg + c;
+          if (res_vec && ch < ch_end) {
+            res[c][0] = reinterpret_cast<const uint4*>(rrow + ch * 16)[0];
+            res[c][1] = reinterpret_cast<const uint4*>(rrow + ch * 16)[1];
+          }
+        }
+      } else {
+        // ---- TMA-store flavour.  The residual tile is staged into the output staging buffer with COALESCED 16-byte loads (consecutive threads
+        // = consecutive bytes of a row; the per-row register loads of the plain flavour touch 32 different 128-byte lines per warp instruction),
+        // one tile AHEAD (`rpf`, loaded while the previous tile was being drained).  Each thread then reads its own row's residual from the
+        // swizzled tile, writes the result back in place, and one thread hands the tile to the TMA.
+        if (et == 0 && it > 0) bulk_wait_read_all();          // the previous tile's TMA store has finished reading the staging buffer
+        epi_bar_sync();
+        if (g.residual != nullptr) {
+          if (it == 0) load_res_tile(tile, rpf);
+#pragma unroll
+          for (int i = 0; i < NPF; ++i) {
+            const int q = et + i * GEMM2_EPI_THREADS, rr = q / (BN / 8), c16 = q - rr * (BN / 8);
+            *reinterpret_cast<uint4*>(stage_out + (c16 >> 2) * (GEMM_BM * 64) + rr * 64 + (((c16 & 3) ^ ((rr >> 1) & 3)) << 4)) = rpf[i];
+          }
         }
       }
-      epi_bar_sync();                                       // bias slice visible to all epilogue threads
+      epi_bar_sync();                                       // bias slice (and the staged residual tile) visible to all epilogue threads
+      if constexpr (TMAO) {
+        if (g.residual != nullptr && it + 1 < n_work) load_res_tile(get_work(it + 1).tile, rpf);     // next tile's residual: in flight during this drain
+      }
       mbar_wait(acc_full(ab), aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ab * ACC_STRIDE + (uint32_t(quarter * 32) << 16);
@@ -466,7 +510,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                   }
                 }
               } else {
-                if (use_res) {
+                uint8_t* srow = nullptr;                   // TMA flavour: this thread's 32-byte slot pair in the staging tile
+                int sw0 = 0, sw1 = 0;
+                if constexpr (TMAO) {
+                  srow = stage_out + (ch >> 1) * (GEMM_BM * 64) + r * 64;
+                  const int k0 = (ch & 1) * 2, sx = (r >> 1) & 3;
+                  sw0 = ((k0 ^ sx) << 4); sw1 = (((k0 + 1) ^ sx) << 4);
+                  if (g.residual != nullptr) {
+                    float f0[8], f1[8];
+                    unpack8(*reinterpret_cast<const uint4*>(srow + sw0), f0, bf); unpack8(*reinterpret_cast<const uint4*>(srow + sw1), f1, bf);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { v[j] += f0[j]; v[8 + j] += f1[j]; }
+                  }
+                } else if (use_res) {
                   if (res_vec) {
                     float f0[8], f1[8];
                     unpack8(res[c][0], f0, bf); unpack8(res[c][1], f1, bf);
@@ -481,16 +537,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] *= g.out_scale;
                 }
-                if (EPI == EPI_STORE && g.epi == EPI_GELU) {
+                if (STOREF && g.epi == EPI_GELU) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
                 }
-                if (EPI == EPI_STORE && g.row_stats != nullptr) {
+                if (STOREF && g.row_stats != nullptr) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) if (full || col0 + j < g.N) { rsum += v[j]; rsq = fmaf(v[j], v[j], rsq); }
                 }
                 uint16_t* crow = reinterpret_cast<uint16_t*>(g.C) + grow * g.ldc + col0;
-                if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+                if constexpr (TMAO) {
+                  float lo[8], hi[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+                  *reinterpret_cast<uint4*>(srow + sw0) = pack8(lo, bf);
+                  *reinterpret_cast<uint4*>(srow + sw1) = pack8(hi, bf);
+                } else if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
                   float lo[8], hi[8];
 #pragma unroll
                   for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
@@ -517,12 +579,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             }
           }
         }
-        if (EPI == EPI_STORE && g.row_stats != nullptr && row_ok && ch_beg < ch_end) {
+        if (STOREF && g.row_stats != nullptr && row_ok && ch_beg < ch_end) {
           atomicAdd(g.row_stats + 2 * grow, rsum); atomicAdd(g.row_stats + 2 * grow + 1, rsq);
+        }
+        if constexpr (TMAO) fence_proxy_async();            // this thread's staging-tile writes -> visible to the TMA (async proxy)
+        if (do_stats || TMAO) epi_bar_sync();
+        if constexpr (TMAO) {
+          if (et == 0) {
+            const int row0 = int(my_row_base(tile));
+#pragma unroll
+            for (int bx = 0; bx < BN / 32; ++bx)
+              if (n0 + bx * 32 < g.N) tma_store_2d(&tmC, smem_base + SM::OUT_OFF + bx * (GEMM_BM * 64), n0 + bx * 32, row0);
+            bulk_commit();
+          }
         }
         if (do_stats) {
           // the four row quarters of this tile were combined in smem: one global reduction per column and statistic
-          epi_bar_sync();
           const long long srow = my_row_base(tile);
           float* dst = g.chan_stats + ((srow / g.stats_rows) * g.N + n0) * 2;
           for (int j = et; j < BN; j += GEMM2_EPI_THREADS)
@@ -532,6 +604,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
       tc_fence_before();
       mbar_arrive(acc_empty(ab));                           // this thread no longer reads accumulator `ab`
     }
+    if constexpr (TMAO) { if (et == 0) bulk_wait_all(); }   // every TMA store of this CTA has landed before the grid can be considered complete
   }
 
   __syncthreads();
