@@ -12,6 +12,7 @@
 
 #include "../../include/cidb200.h"
 #include "attn_cross.cuh"
+#include "attn_cross2.cuh"         // persistent / pipelined flavour for head dims <= 80
 #include "attn_tc5.cuh"           // one 128-row query tile per CTA: head dims > 80 and short sequences
 #ifndef CID_ATTN_NO_V6
 #include "attn_tc6.cuh"           // two query tiles per CTA, P in tensor memory (aliasing S): head dim 80, >= 256 queries
@@ -130,6 +131,39 @@ bool g_tma_epilogue = false;      // A/B builds: register epilogue everywhere
 #else
 bool g_tma_epilogue = true;
 #endif
+int g_tma_epilogue_max_kb = 24;
+bool g_cross2 = true;
+
+// N tile of the store / GELU / QKV flavours (their operand layouts do not depend on the tile; GEGLU's interleaved weight does, so it keeps
+// cid_gemm_tile_n).  Picks between the 256- and 160-wide tiles by a wave model: cost = waves x BN x (cost per column), where a tail wave
+// counts 1 unless the tail-balancing split applies (1/sp + fix-up), and a 160-wide tile pays ~10 % more per column (more L2->SMEM bytes
+// per FLOP).  N = 1280 at 32 row tiles is 160 tiles of 256 (1.08 waves -> 2) but 256 tiles of 160 (1.73 waves -> 2): 0.69x the time.
+#ifndef CID_TILE_STATIC
+double tile_cost(int bn, int N, int m_tiles, int num_kb, bool ws) {
+  const int G = num_sms();
+  const int total = ((N + bn - 1) / bn) * m_tiles;
+  const int full = total / G, tail = total % G;
+  double waves = full;
+  if (tail) {
+    int sp = 1;
+    if (ws && g_splitk_max > 1) {
+      sp = G / tail;
+      if (sp > num_kb / g_splitk_min_kb) sp = num_kb / g_splitk_min_kb;
+      if (sp > g_splitk_max) sp = g_splitk_max;
+    }
+    waves += sp >= 2 ? 1.0 / sp + 0.15 : 1.0;
+  }
+  return waves * bn * (bn == 256 ? 1.0 : 1.1);
+}
+#endif
+int pick_tile_n(int N, int epi, int m_tiles, int num_kb, bool ws) {
+  const int fixed = cid_gemm_tile_n(N, epi);
+#ifndef CID_TILE_STATIC
+  if (epi != CID_EPI_GEGLU && fixed == 256 && N % 160 == 0 && tile_cost(160, N, m_tiles, num_kb, ws) < tile_cost(256, N, m_tiles, num_kb, ws))
+    return 160;
+#endif
+  return fixed;
+}
 
 template <int BN, int STAGES, int EPI, int BF>
 int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& c, const GemmArgs& g, int grid,
@@ -173,8 +207,11 @@ int launch_gemm2_any(const CUtensorMap& a1, const CUtensorMap& a2, const CUtenso
   if constexpr (BN >= 32) {
     if (flavour == EPI_GEGLU) return CID_G2(STAGES, EPI_GEGLU);
     if (flavour == EPI_QKV) return CID_G2(STAGES, EPI_QKV);
-    // store epilogue through shared memory + TMA whenever the caller could build an output map and no tail tile is split
-    if (c_out != nullptr && sched.ksplit == 1 && g_tma_epilogue) return CID_G2(STAGES_T, EPI_STORE_TMA);
+    // Store epilogue through shared memory + TMA for SHORT K loops only (K <= 1536, where the epilogue is a large share of the tile): its
+    // staging tile costs one operand-ring stage, which long K loops miss more than they gain from the coalesced stores.  Measured A/B in
+    // profiles/r02_tma_epilogue_ab.txt: 8192x1280x1280 51.6 -> 44.0 us, 65536x320x320 -13 %, but 8192x1280x5120 116 -> 126 us.
+    const int num_kb_all = g.taps * (g.kblocks_a1 + g.kblocks_a2);
+    if (c_out != nullptr && sched.ksplit == 1 && g_tma_epilogue && num_kb_all <= g_tma_epilogue_max_kb) return CID_G2(STAGES_T, EPI_STORE_TMA);
   } else {
     if (flavour != EPI_STORE) return fail(CID_ERR_UNSUPPORTED, "GEGLU / QKV epilogues need an N tile >= 32");
   }
@@ -272,6 +309,24 @@ int launch_attn_cross(const CUtensorMap& q, const CUtensorMap& k, const CUtensor
   return 0;
 }
 
+template <int D_PAD>
+int launch_attn_cross2(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a, long long units, cudaStream_t st) {
+  using C = Cross2Cfg<D_PAD>;
+  static bool configured[2][MAX_DEVICES] = {};
+  const int grid = units < num_sms() ? int(units) : num_sms();
+  // the CTA allocates all 512 TMEM columns: ask for more than half an SM's shared memory so that two of them never share an SM
+  constexpr int SMEM = C::TOTAL > 117 * 1024 ? C::TOTAL : 117 * 1024;
+  if (a.is_bf16) {
+    if (int rc = set_smem(attn_cross2_kernel<D_PAD, 1>, SMEM, "attn_cross2_kernel", configured[1])) return rc;
+    launch_pdl(attn_cross2_kernel<D_PAD, 1>, dim3(grid), dim3(CROSS2_THREADS), SMEM, st, q, k, v, a);
+  } else {
+    if (int rc = set_smem(attn_cross2_kernel<D_PAD, 0>, SMEM, "attn_cross2_kernel", configured[0])) return rc;
+    launch_pdl(attn_cross2_kernel<D_PAD, 0>, dim3(grid), dim3(CROSS2_THREADS), SMEM, st, q, k, v, a);
+  }
+  CID_CHECK_LAUNCH("attn_cross2_kernel");
+  return 0;
+}
+
 // Q/K style map: [B, N, H, d] view, row pitch `pitch` elements, box {64, box_rows, 1, 1}
 int map_qk(CUtensorMap* m, const void* base, int B, int N, int H, int d, long long pitch, int box_rows) {
   cuuint64_t dims[4] = {cuuint64_t(d), cuuint64_t(N), cuuint64_t(H), cuuint64_t(B)};
@@ -318,7 +373,7 @@ int cid_gemm(const void* A, long long lda, const void* A2, long long lda2, int K
   if (int rc = check_ws(workspace, ws_bytes, "cid_gemm")) return rc;
   if (K1 <= 0 || K1 % 64 || K2 < 0 || K2 % 64) return fail(CID_ERR_ARG, "cid_gemm: K1=%d K2=%d must be multiples of 64", K1, K2);
   if (K2 > 0 && !A2) return fail(CID_ERR_ARG, "cid_gemm: K2 > 0 without A2");
-  const int bn = cid_gemm_tile_n(N, epi);
+  const int bn = pick_tile_n(N, epi, (M + GEMM_BM - 1) / GEMM_BM, (K1 + K2) / 64, workspace != nullptr);
   if (bn < 0) return fail(CID_ERR_UNSUPPORTED, "cid_gemm: GEGLU needs N %% 64 == 0 (N=%d)", N);
   if (epi == CID_EPI_QKV && (!Vt || n_split % 32 || heads <= 0 || hdim <= 0 || ntok <= 0 || M % ntok))
     return fail(CID_ERR_ARG, "cid_gemm: bad QKV epilogue arguments");
@@ -364,7 +419,7 @@ int cid_conv3x3(const void* X, const void* Wt, void* Y, long long ldy, int NB, i
   g.tiles_x = (W + g.TW - 1) / g.TW; g.tiles_y = (H + g.TH - 1) / g.TH;
   const int tiles_n = (NB + g.TN - 1) / g.TN;
   const int m_tiles = g.tiles_x * g.tiles_y * tiles_n;
-  const int bn = cid_gemm_tile_n(Cout, CID_EPI_STORE);
+  const int bn = pick_tile_n(Cout, CID_EPI_STORE, m_tiles, 9 * Cin / 64, workspace != nullptr);
   CUtensorMap ta, tb;
   int rc;
   if (!stride2) {
@@ -454,6 +509,18 @@ int cid_attn_cross(const void* Q, long long q_pitch, const void* Kcat, const voi
   AttnArgs a{}; a.B = B; a.H = H; a.Nq = N; a.Nkv = 96; a.d = d; a.scale_log2 = 1.4426950408889634f / sqrtf(float(d));
   a.O = O; a.ldo = ldo; a.is_bf16 = dtype == CID_BF16; a.n_text = n_text; a.ip_off = 80; a.n_ip = n_ip; a.ip_scale = ip_scale;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+#ifndef CID_CROSS_V1
+  // persistent pipelined flavour wherever there is at least one unit per SM (smaller problems: one short CTA per unit is as good)
+  const long long units = (long long)B * H * ((N + 127) / 128);
+  if (dp <= 80 && units >= num_sms() && g_cross2) {
+    switch (dp) {
+      case 32: return launch_attn_cross2<32>(tq, tk, tv, a, units, st);
+      case 48: return launch_attn_cross2<48>(tq, tk, tv, a, units, st);
+      case 64: return launch_attn_cross2<64>(tq, tk, tv, a, units, st);
+      case 80: return launch_attn_cross2<80>(tq, tk, tv, a, units, st);
+    }
+  }
+#endif
   switch (dp) {
     case 32: return launch_attn_cross<32>(tq, tk, tv, a, st);
     case 48: return launch_attn_cross<48>(tq, tk, tv, a, st);

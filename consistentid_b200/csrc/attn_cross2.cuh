@@ -1,0 +1,279 @@
+// attn_cross2_kernel - the decoupled text + id cross-attention of Consistent_IPAttProcessor (attention.py:259-279), same operands and
+// results as attn_cross_kernel (attn_cross.cuh), restructured as a PERSISTENT, PIPELINED kernel for head dims <= 80.
+//
+// attn_cross_kernel runs one CTA per (128-query tile, head, sample) and that CTA walks a strictly serial chain (TMA Q/K/V -> S MMA ->
+// softmax -> P through shared memory -> P.V MMA -> epilogue): ~6 000 SM cycles per tile against ~800 cycles of exponentials and
+// ~900 cycles of HBM time - 75-110 TF/s, 14 % of HBM (profiles/r02_shapes_*).  Here every SM keeps ONE CTA that owns a contiguous,
+// balanced range of the launch's (sample, head, query tile) units and overlaps them:
+//   * warp 0 streams Q tiles through a 4-slot ring and K_cat / V_cat^T through a 2-slot ring (reloaded only when (sample, head) changes);
+//   * warp 1 issues, per unit u, S(u) = Q K_cat^T into TMEM buffer u & 1 and then P.V(u-1) of the other buffer;
+//   * two softmax warpgroups (warps 2-5 / 6-9) own one TMEM buffer each: pull the 96 score columns into registers, two masked softmaxes
+//     (text keys [0, n_text), id keys [80, 80 + n_ip)), write P as packed 16-bit pairs over the first 48 score columns (TMEM is the A
+//     operand of the P.V MMAs - no shared-memory round trip, no CTA-wide barrier), later drain O_text / O_ip, mix and store.
+// TMEM (2 x 256 columns): per buffer [S 96 (P aliases 0..47) | O_text D_PAD | O_ip D_PAD].
+#pragma once
+#include "attn_common.cuh"
+#include "attn_tc7.cuh"          // tmem_st_x16 / tmem_st_wait
+
+namespace cid {
+
+constexpr int CROSS2_THREADS = 320;
+
+template <int D_PAD>
+struct Cross2Cfg {
+  static_assert(D_PAD % 16 == 0 && D_PAD <= 80, "attn_cross2 covers head dims <= 80");
+  static constexpr int NCH = (D_PAD + 63) / 64;
+  static constexpr int NQ = 4;                                   // Q ring slots
+  static constexpr int KROWS = 96;
+  static constexpr int Q_BYTES = NCH * 16384;
+  static constexpr int K_CHUNK = KROWS * 128;
+  static constexpr int K_BYTES = NCH * K_CHUNK;
+  static constexpr int V_CHUNK = D_PAD * 128;
+  static constexpr int V_BYTES = 2 * V_CHUNK;
+  static constexpr int OFF_K = NQ * Q_BYTES;
+  static constexpr int OFF_V = OFF_K + 2 * K_BYTES;
+  static constexpr int OFF_BAR = OFF_V + 2 * V_BYTES;
+  static constexpr int TOTAL = OFF_BAR + 256;
+  static constexpr int TM_BUF = 256, TM_OT = 96, TM_OI = 96 + D_PAD;
+  static_assert(TM_OI + D_PAD <= TM_BUF, "TMEM budget");
+  static_assert(K_CHUNK % 1024 == 0 && V_CHUNK % 1024 == 0, "128B-swizzle atoms need 1 KB aligned chunks");
+};
+
+template <int D_PAD, int BF>
+__global__ void __launch_bounds__(CROSS2_THREADS, 1)
+attn_cross2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmVt, const AttnArgs a) {
+  using C = Cross2Cfg<D_PAD>;
+  constexpr int NQ = C::NQ;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if ((sbase & 1023u) != 0) { if (threadIdx.x == 0) printf("cid: cross-attn smem base not 1024-aligned\n"); __trap(); }
+  const uint32_t bar0 = sbase + C::OFF_BAR;
+  auto q_full = [&](int s) { return bar0 + 8u * s; };
+  auto q_free = [&](int s) { return bar0 + 8u * (NQ + s); };
+  auto kv_full = [&](int s) { return bar0 + 8u * (2 * NQ + s); };
+  auto kv_free = [&](int s) { return bar0 + 8u * (2 * NQ + 2 + s); };
+  auto s_full = [&](int j) { return bar0 + 8u * (2 * NQ + 4 + j); };       // S(u) complete (MMA commit)
+  auto p_ready = [&](int j) { return bar0 + 8u * (2 * NQ + 6 + j); };      // P(u) in TMEM (128 softmax threads)
+  auto o_full = [&](int j) { return bar0 + 8u * (2 * NQ + 8 + j); };       // P.V(u) retired (MMA commit)
+  auto o_free = [&](int j) { return bar0 + 8u * (2 * NQ + 10 + j); };      // O(u) pulled into registers (128 softmax threads)
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + C::OFF_BAR + 8 * (2 * NQ + 12));
+  static_assert(8 * (2 * NQ + 13) <= 256, "barrier block");
+
+  const int warp = warp_id(), lane = lane_id();
+  // this CTA's contiguous range of units; unit g = (sample * H + head) * tiles + query tile
+  const int tiles = (a.Nq + 127) / 128;
+  const long long U = (long long)a.B * a.H * tiles;
+  const int g_beg = int(U * blockIdx.x / gridDim.x), g_end = int(U * (blockIdx.x + 1) / gridDim.x);
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmVt); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < NQ; ++s) { mbar_init(q_full(s), 1); mbar_init(q_free(s), 1); }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(kv_full(s), 1); mbar_init(kv_free(s), 1);
+        mbar_init(s_full(s), 1); mbar_init(p_ready(s), 128); mbar_init(o_full(s), 1); mbar_init(o_free(s), 128);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  griddep_wait();                  // PDL: the prologue above overlaps the predecessor's tail
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    int n_kv = -1;                 // index of the current K/V group (one per (sample, head) run inside the range)
+    int uq = 0;
+    for (int g = g_beg; g < g_end; ++g, ++uq) {
+      const int bh = g / tiles, t = g - bh * tiles;
+      const int b = bh / a.H, h = bh - b * a.H;
+      if (g == g_beg || t == 0) {
+        ++n_kv;
+        const int s = n_kv & 1;
+        mbar_wait(kv_free(s), uint32_t(((n_kv >> 1) & 1) ^ 1));
+        const uint32_t kb = kv_full(s), kd = sbase + C::OFF_K + s * C::K_BYTES, vd = sbase + C::OFF_V + s * C::V_BYTES;
+        if (elect_one()) {
+          mbar_expect_tx(kb, C::K_BYTES + C::V_BYTES);
+#pragma unroll
+          for (int ch = 0; ch < C::NCH; ++ch) tma_load_4d(kd + ch * C::K_CHUNK, &tmK, kb, ch * 64, 0, h, b);
+#pragma unroll
+          for (int kc = 0; kc < 2; ++kc) tma_load_3d(vd + kc * C::V_CHUNK, &tmVt, kb, kc * 64, 0, bh);
+        }
+        __syncwarp();
+      }
+      const int slot = uq % NQ;
+      mbar_wait(q_free(slot), uint32_t(((uq / NQ) & 1) ^ 1));
+      const uint32_t qb = q_full(slot), qd = sbase + slot * C::Q_BYTES;
+      if (elect_one()) {
+        mbar_expect_tx(qb, C::Q_BYTES);
+#pragma unroll
+        for (int ch = 0; ch < C::NCH; ++ch) tma_load_4d(qd + ch * 16384, &tmQ, qb, ch * 64, t * 128, h, b);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) griddep_launch_dependents();
+    __syncwarp();
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    const uint32_t idesc_s = make_idesc(128, C::KROWS, BF);
+    const uint32_t idesc_pv = make_idesc(128, D_PAD, BF);
+    const bool has_ip = a.n_ip > 0;
+    // P.V of unit x (its K/V slot kvs; `last`: the K/V group ends with it).  Text keys [0, 80) = k-steps 0-4 into O_text; keys [80, 96) =
+    // k-step 5 into O_ip, or - without id tokens (plain cross-attention over up to 96 rows) - more text keys.
+    auto issue_PV = [&](int x, int kvs, bool last) {
+      const int j = x & 1;
+      const uint32_t par = uint32_t((x >> 1) & 1);
+      mbar_wait(p_ready(j), par);
+      mbar_wait(o_free(j), par ^ 1u);
+      tc_fence_after();
+      const uint32_t tb = tmem + j * C::TM_BUF;
+      const uint32_t sv = sbase + C::OFF_V + kvs * C::V_BYTES;
+      const uint32_t ob = o_full(j), fb = kv_free(kvs);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks)
+          umma_ts(tb + C::TM_OT, tb + ks * 8, make_desc_sw128(sv + (ks >> 2) * C::V_CHUNK + (ks & 3) * 32), idesc_pv, ks ? 1u : 0u);
+        umma_ts(tb + (has_ip ? C::TM_OI : C::TM_OT), tb + 5 * 8, make_desc_sw128(sv + C::V_CHUNK + 32), idesc_pv, has_ip ? 0u : 1u);
+        umma_commit(ob);
+        if (last) umma_commit(fb);
+      }
+      __syncwarp();
+    };
+    int n_kv = -1, u = 0;
+    int prev_kvs = 0; bool prev_last = false;
+    for (int g = g_beg; g < g_end; ++g, ++u) {
+      const int t = g % tiles;
+      if (g == g_beg || t == 0) {
+        ++n_kv;
+        mbar_wait(kv_full(n_kv & 1), uint32_t((n_kv >> 1) & 1));
+      }
+      const int kvs = n_kv & 1;
+      const int slot = u % NQ;
+      mbar_wait(q_full(slot), uint32_t((u / NQ) & 1));
+      tc_fence_after();
+      {
+        const int j = u & 1;
+        const uint32_t d_tm = tmem + j * C::TM_BUF, sq = sbase + slot * C::Q_BYTES, sk = sbase + C::OFF_K + kvs * C::K_BYTES;
+        const uint32_t sb = s_full(j), qb = q_free(slot);
+        if (elect_one()) {
+#pragma unroll
+          for (int ch = 0; ch < C::NCH; ++ch) {
+            const int ksteps = (D_PAD - ch * 64 >= 64) ? 4 : (D_PAD - ch * 64) / 16;
+#pragma unroll
+            for (int kk = 0; kk < ksteps; ++kk)
+              umma_ss(d_tm, make_desc_sw128(sq + ch * 16384 + kk * 32), make_desc_sw128(sk + ch * C::K_CHUNK + kk * 32), idesc_s, (ch | kk) ? 1u : 0u);
+          }
+          umma_commit(sb);
+          umma_commit(qb);
+        }
+        __syncwarp();
+      }
+      if (u > 0) issue_PV(u - 1, prev_kvs, prev_last);
+      prev_kvs = kvs;
+      prev_last = (g + 1 == g_end) || ((g + 1) % tiles == 0);
+    }
+    if (u > 0) issue_PV(u - 1, prev_kvs, prev_last);
+  } else {
+    // ============================================================ softmax warpgroups (warps 2-5: even units, warps 6-9: odd units)
+    const int wg = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = uint32_t(quarter * 32) << 16;
+    const uint32_t tS = tmem + wg * C::TM_BUF + lane_off;
+    const float c = a.scale_log2;
+    const int t_end = a.n_text, i_beg = a.ip_off, i_end = a.ip_off + a.n_ip;
+    const bool has_ip = a.n_ip > 0;
+    int k = 0;                                            // uses of this warpgroup's buffer so far
+    for (int g = g_beg + wg; g < g_end; g += 2, ++k) {
+      const int bh = g / tiles, t = g - bh * tiles;
+      const int b = bh / a.H, h = bh - b * a.H;
+      const uint32_t par = uint32_t(k & 1);
+      mbar_wait(s_full(wg), par);
+      tc_fence_after();
+      uint32_t v[96];
+      {
+        uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+        uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+        uint32_t (&v2)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[64]);
+        tmem_ld_x32(tS + 0, v0);
+        tmem_ld_x32(tS + 32, v1);
+        tmem_ld_x32(tS + 64, v2);
+        tmem_ld_wait();
+      }
+      float mt = -INFINITY, mi = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 96; ++i) {
+        const float s = __uint_as_float(v[i]);
+        if (i < t_end) mt = fmaxf(mt, s);
+        if (i >= i_beg && i < i_end) mi = fmaxf(mi, s);
+      }
+      const float nmt = -mt * c, nmi = -mi * c;
+      float lt = 0.f, li = 0.f;
+      uint32_t pk[48];
+#pragma unroll
+      for (int i = 0; i < 96; i += 2) {
+        float p[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = i + e; const float s = __uint_as_float(v[key]);
+          float pe = 0.f;
+          if (key < t_end) { pe = fast_exp2(fmaf(s, c, nmt)); lt += pe; }
+          else if (key >= i_beg && key < i_end) { pe = fast_exp2(fmaf(s, c, nmi)); li += pe; }
+          p[e] = pe;
+        }
+        pk[i >> 1] = pack16(p[0], p[1], BF);
+      }
+#pragma unroll
+      for (int cc = 0; cc < 48; cc += 16) {
+        uint32_t (&p16)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[cc]);
+        tmem_st_x16(tS + cc, p16);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_ready(wg));
+      // ---- drain O_text / O_ip, mix, store (each branch rounded to 16 bits before the mix: attention.py:264,276-279)
+      const float wt = 1.f / lt, wi = has_ip ? 1.f / li : 0.f, sc = has_ip ? a.ip_scale : 0.f;
+      const int row = t * 128 + r;
+      const bool row_ok = row < a.Nq;
+      uint16_t* dst = reinterpret_cast<uint16_t*>(a.O) + ((long long)b * a.Nq + row) * a.ldo + h * a.d;
+      mbar_wait(o_full(wg), par);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < D_PAD; cc += 16) {
+        uint32_t vt[16], vi[16];
+        tmem_ld_x16(tS + C::TM_OT + cc, vt);
+        if (has_ip) tmem_ld_x16(tS + C::TM_OI + cc, vi);
+        tmem_ld_wait();
+        if (cc + 16 >= D_PAD) { tc_fence_before(); mbar_arrive(o_free(wg)); }     // accumulators are in registers: the buffer may be reused
+        if (row_ok && cc < a.d) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float tt = unpack16(pack16(__uint_as_float(vt[i]) * wt, 0.f, BF), BF).x;
+            const float ii = has_ip ? unpack16(pack16(__uint_as_float(vi[i]) * wi, 0.f, BF), BF).x : 0.f;
+            f[i] = tt + sc * ii;
+          }
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (cc + q * 8 < a.d) {
+              uint4 o;
+              o.x = pack16(f[q * 8 + 0], f[q * 8 + 1], BF); o.y = pack16(f[q * 8 + 2], f[q * 8 + 3], BF);
+              o.z = pack16(f[q * 8 + 4], f[q * 8 + 5], BF); o.w = pack16(f[q * 8 + 6], f[q * 8 + 7], BF);
+              *reinterpret_cast<uint4*>(dst + cc + q * 8) = o;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<512>(tmem); }
+}
+
+}  // namespace cid

@@ -272,7 +272,7 @@ def check_attn_cross(B=2, H=2, N=256, d=64, dtype=torch.float16, n_text=77, n_ip
     C = H * d
     q = _rand((B * N, C), dtype, seed)
     kt, vt_ = _rand((B * n_text, C), dtype, seed + 1), _rand((B * n_text, C), dtype, seed + 2)
-    ki, vi = _rand((B * n_ip, C), dtype, seed + 3), _rand((B * n_ip, C), dtype, seed + 4)
+    ki, vi = (_rand((B * n_ip, C), dtype, seed + 3), _rand((B * n_ip, C), dtype, seed + 4)) if n_ip else (None, None)
     k_cat = torch.full((B, 96, C), float("nan"), dtype=dtype, device=DEV)
     vt_cat = torch.full((B * H, d, 96), float("nan"), dtype=dtype, device=DEV)
     ops.pack_cross_kv(kt, vt_, ki, vi, k_cat, vt_cat, B, C, H, n_text, n_ip)
@@ -284,7 +284,7 @@ def check_attn_cross(B=2, H=2, N=256, d=64, dtype=torch.float16, n_text=77, n_ip
         return t.float().reshape(B, n, H, d).transpose(1, 2)
     qh = heads(q, N)
     o1 = torch.softmax(qh @ heads(kt, n_text).transpose(-1, -2) * d ** -0.5, -1) @ heads(vt_, n_text)
-    o2 = torch.softmax(qh @ heads(ki, n_ip).transpose(-1, -2) * d ** -0.5, -1) @ heads(vi, n_ip)
+    o2 = torch.softmax(qh @ heads(ki, n_ip).transpose(-1, -2) * d ** -0.5, -1) @ heads(vi, n_ip) if n_ip else 0.0
     ref = (o1 + ip_scale * o2).transpose(1, 2).reshape(B * N, C)
     return _report(f"attn_cross B{B} H{H} N{N} d{d} {str(dtype)[6:]} s{ip_scale}", out, ref, 1e-2)
 
@@ -540,6 +540,14 @@ CHECKS = {
     "attn_cross_d80": (check_attn_cross, dict(B=1, H=4, N=200, d=80)),
     "attn_cross_d160": (check_attn_cross, dict(B=2, H=2, N=64, d=160, dtype=B16)),
     "attn_cross_d32": (check_attn_cross, dict(B=2, H=2, N=128, d=32)),
+    "attn_cross_noip": (check_attn_cross, dict(B=2, H=2, N=256, d=64, n_text=81, n_ip=0)),
+    # >= one (sample, head, 128-query tile) unit per SM: the persistent pipelined flavour (attn_cross2.cuh)
+    "attn_cross2_d40": (check_attn_cross, dict(B=4, H=8, N=4096, d=40, ip_scale=0.7)),
+    "attn_cross2_d64_bf16_ragged": (check_attn_cross, dict(B=4, H=10, N=1000, d=64, dtype=B16)),
+    "attn_cross2_d80": (check_attn_cross, dict(B=4, H=8, N=1024, d=80, ip_scale=1.3)),
+    "attn_cross2_d64_tail": (check_attn_cross, dict(B=3, H=7, N=1160, d=64, n_ip=16, n_text=80)),
+    "attn_cross2_noip": (check_attn_cross, dict(B=2, H=20, N=1024, d=64, n_text=96, n_ip=0)),
+    "attn_cross2_d32": (check_attn_cross, dict(B=8, H=4, N=640, d=32)),
     "conv_stats": (check_conv_stats, dict(NB=2, H=16, W=16, Cin=128, Cout=320)),
     "conv_stats_1280": (check_conv_stats, dict(NB=3, H=16, W=16, Cin=64, Cout=1280, dtype=B16, residual=False)),
     "conv_stats_w128": (check_conv_stats, dict(NB=1, H=4, W=128, Cin=64, Cout=160)),
