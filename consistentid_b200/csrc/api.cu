@@ -508,6 +508,9 @@ int cid_attn_cross(const void* Q, long long q_pitch, const void* Kcat, const voi
   if ((rc = map_vt(&tv, Vtcat, B * H, d, 96, dp))) return rc;
   AttnArgs a{}; a.B = B; a.H = H; a.Nq = N; a.Nkv = 96; a.d = d; a.scale_log2 = 1.4426950408889634f / sqrtf(float(d));
   a.O = O; a.ldo = ldo; a.is_bf16 = dtype == CID_BF16; a.n_text = n_text; a.ip_off = 80; a.n_ip = n_ip; a.ip_scale = ip_scale;
+#ifdef CID_ATTN_TRACE
+  a.trace = g_attn_trace;
+#endif
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #ifndef CID_CROSS_V1
   // persistent pipelined flavour wherever there is at least one unit per SM (smaller problems: one short CTA per unit is as good)

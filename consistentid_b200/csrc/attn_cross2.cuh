@@ -18,6 +18,11 @@
 namespace cid {
 
 constexpr int CROSS2_THREADS = 320;
+#ifndef CID_CROSS2_STAGGER
+#define CID_CROSS2_STAGGER 0
+#endif
+constexpr long long CROSS2_STAGGER_CYCLES = CID_CROSS2_STAGGER;
+constexpr int CROSS_IP_OFF = 80;                       // first id key row of K_cat / V_cat (cid_pack_cross_kv, cid_attn_cross: ip_off is always 80)
 
 template <int D_PAD>
 struct Cross2Cfg {
@@ -146,7 +151,14 @@ attn_cross2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     };
     int n_kv = -1, u = 0;
     int prev_kvs = 0; bool prev_last = false;
+#ifdef CID_ATTN_TRACE
+    const bool trm = a.trace != nullptr && blockIdx.x < 16 && lane == 0;
+    auto mstamp = [&](int u_, int e) { if (trm && u_ < 64) a.trace[((size_t)(32 + blockIdx.x) * 64 + u_) * 8 + e] = clock64(); };
+#else
+    auto mstamp = [&](int, int) {};
+#endif
     for (int g = g_beg; g < g_end; ++g, ++u) {
+      mstamp(u, 0);
       const int t = g % tiles;
       if (g == g_beg || t == 0) {
         ++n_kv;
@@ -156,6 +168,7 @@ attn_cross2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int slot = u % NQ;
       mbar_wait(q_full(slot), uint32_t((u / NQ) & 1));
       tc_fence_after();
+      mstamp(u, 1);
       {
         const int j = u & 1;
         const uint32_t d_tm = tmem + j * C::TM_BUF, sq = sbase + slot * C::Q_BYTES, sk = sbase + C::OFF_K + kvs * C::K_BYTES;
@@ -173,7 +186,9 @@ attn_cross2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         __syncwarp();
       }
+      mstamp(u, 2);
       if (u > 0) issue_PV(u - 1, prev_kvs, prev_last);
+      mstamp(u, 3);
       prev_kvs = kvs;
       prev_last = (g + 1 == g_end) || ((g + 1) % tiles == 0);
     }
@@ -186,15 +201,30 @@ attn_cross2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t lane_off = uint32_t(quarter * 32) << 16;
     const uint32_t tS = tmem + wg * C::TM_BUF + lane_off;
     const float c = a.scale_log2;
-    const int t_end = a.n_text, i_beg = a.ip_off, i_end = a.ip_off + a.n_ip;
+    const int t_end = a.n_text, i_end = CROSS_IP_OFF + a.n_ip;
     const bool has_ip = a.n_ip > 0;
     int k = 0;                                            // uses of this warpgroup's buffer so far
+    // Anti-phase start: both warpgroups would otherwise receive their first scores together and stay in lock-step - exponentials (MUFU)
+    // contended, then both draining O with the MUFU idle (profiles/r02_trace_cross2_inphase_*.txt: 2 300-cycle exp phases, ~4 600 cycles
+    // per pair of units).  Half a period of head start for warpgroup 0 makes one warpgroup's exponentials run under the other's drain.
+    if (CROSS2_STAGGER_CYCLES > 0 && wg == 1) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < CROSS2_STAGGER_CYCLES) { }
+    }
+#ifdef CID_ATTN_TRACE
+    const bool tr = a.trace != nullptr && blockIdx.x < 16 && quarter == 0 && lane == 0;
+    auto stamp = [&](int k_, int e) { if (tr && k_ < 64) a.trace[((size_t)(blockIdx.x * 2 + wg) * 64 + k_) * 8 + e] = clock64(); };
+#else
+    auto stamp = [&](int, int) {};
+#endif
     for (int g = g_beg + wg; g < g_end; g += 2, ++k) {
+      stamp(k, 0);
       const int bh = g / tiles, t = g - bh * tiles;
       const int b = bh / a.H, h = bh - b * a.H;
       const uint32_t par = uint32_t(k & 1);
       mbar_wait(s_full(wg), par);
       tc_fence_after();
+      stamp(k, 1);
       uint32_t v[96];
       {
         uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
@@ -205,15 +235,21 @@ attn_cross2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld_x32(tS + 64, v2);
         tmem_ld_wait();
       }
-      float mt = -INFINITY, mi = -INFINITY;
+      stamp(k, 2);
+      // Both masked softmaxes BRANCH-FREE (selects on the key index): with `if (key < n_text) ...` inside the unrolled loops nvcc emits a
+      // real branch + reconvergence pair per element - measured 35 / 54 cycles per element in the max / exp passes
+      // (profiles/r02_trace_cross2_branchy_*.txt), 8 600 cycles per unit where the MUFU needs ~800.
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, mi = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 96; ++i) {
         const float s = __uint_as_float(v[i]);
-        if (i < t_end) mt = fmaxf(mt, s);
-        if (i >= i_beg && i < i_end) mi = fmaxf(mi, s);
+        m4[i & 3] = fmaxf(m4[i & 3], i < t_end ? s : -INFINITY);
+        if (i >= CROSS_IP_OFF) mi = fmaxf(mi, i < i_end ? s : -INFINITY);
       }
+      const float mt = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       const float nmt = -mt * c, nmi = -mi * c;
-      float lt = 0.f, li = 0.f;
+      stamp(k, 3);
+      float l4[4] = {0.f, 0.f, 0.f, 0.f}, li = 0.f;
       uint32_t pk[48];
 #pragma unroll
       for (int i = 0; i < 96; i += 2) {
@@ -221,13 +257,22 @@ attn_cross2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int key = i + e; const float s = __uint_as_float(v[key]);
-          float pe = 0.f;
-          if (key < t_end) { pe = fast_exp2(fmaf(s, c, nmt)); lt += pe; }
-          else if (key >= i_beg && key < i_end) { pe = fast_exp2(fmaf(s, c, nmi)); li += pe; }
-          p[e] = pe;
+          if (key < CROSS_IP_OFF) {                        // compile-time: text keys or padding
+            const float x = fmaf(s, c, nmt);
+            p[e] = fast_exp2(key < t_end ? x : -INFINITY);
+            l4[(i >> 1) & 3] += p[e];
+          } else {                                         // id keys, padding, or (no id tokens) more text keys
+            const bool is_t = key < t_end, is_i = key < i_end;
+            const float x = fmaf(s, c, is_t ? nmt : nmi);
+            p[e] = fast_exp2((is_t || is_i) ? x : -INFINITY);
+            l4[(i >> 1) & 3] += is_t ? p[e] : 0.f;
+            li += is_t ? 0.f : p[e];
+          }
         }
         pk[i >> 1] = pack16(p[0], p[1], BF);
       }
+      const float lt = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      stamp(k, 4);
 #pragma unroll
       for (int cc = 0; cc < 48; cc += 16) {
         uint32_t (&p16)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[cc]);
@@ -236,6 +281,7 @@ attn_cross2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_ready(wg));
+      stamp(k, 5);
       // ---- drain O_text / O_ip, mix, store (each branch rounded to 16 bits before the mix: attention.py:264,276-279)
       const float wt = 1.f / lt, wi = has_ip ? 1.f / li : 0.f, sc = has_ip ? a.ip_scale : 0.f;
       const int row = t * 128 + r;
@@ -243,6 +289,7 @@ attn_cross2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       uint16_t* dst = reinterpret_cast<uint16_t*>(a.O) + ((long long)b * a.Nq + row) * a.ldo + h * a.d;
       mbar_wait(o_full(wg), par);
       tc_fence_after();
+      stamp(k, 6);
 #pragma unroll
       for (int cc = 0; cc < D_PAD; cc += 16) {
         uint32_t vt[16], vi[16];
@@ -253,10 +300,13 @@ attn_cross2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (row_ok && cc < a.d) {
           float f[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float tt = unpack16(pack16(__uint_as_float(vt[i]) * wt, 0.f, BF), BF).x;
-            const float ii = has_ip ? unpack16(pack16(__uint_as_float(vi[i]) * wi, 0.f, BF), BF).x : 0.f;
-            f[i] = tt + sc * ii;
+          for (int i = 0; i < 16; i += 2) {               // each branch rounded to 16 bits before the mix, two values per conversion
+            const float2 tt = unpack16(pack16(__uint_as_float(vt[i]) * wt, __uint_as_float(vt[i + 1]) * wt, BF), BF);
+            f[i] = tt.x; f[i + 1] = tt.y;
+            if (has_ip) {
+              const float2 ii = unpack16(pack16(__uint_as_float(vi[i]) * wi, __uint_as_float(vi[i + 1]) * wi, BF), BF);
+              f[i] = fmaf(sc, ii.x, tt.x); f[i + 1] = fmaf(sc, ii.y, tt.y);
+            }
           }
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
@@ -269,6 +319,7 @@ attn_cross2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
       }
+      stamp(k, 7);
     }
     tc_fence_before();
   }
