@@ -133,6 +133,9 @@ bool g_tma_epilogue = true;
 #endif
 int g_tma_epilogue_max_kb = 24;
 bool g_cross2 = true;
+#ifdef CID_GEMM_TRACE
+long long* g_gemm_trace = nullptr;       // debug builds only (tools/trace_gemm.py)
+#endif
 
 // N tile of the store / GELU / QKV flavours (their operand layouts do not depend on the tile; GEGLU's interleaved weight does, so it keeps
 // cid_gemm_tile_n).  Picks between the 256- and 160-wide tiles by a wave model: cost = waves x BN x (cost per column), where a tail wave
@@ -171,7 +174,12 @@ int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap
   using SM = Gemm2Smem<BN, STAGES, EPI == EPI_STORE_TMA>;
   static bool configured[MAX_DEVICES] = {};
   if (int rc = set_smem(gemm_tc2_kernel<BN, STAGES, EPI, BF>, SM::TOTAL, "gemm_tc2_kernel", configured)) return rc;
+#ifdef CID_GEMM_TRACE
+  GemmArgs gt = g; gt.trace = g_gemm_trace;
+  launch_pdl(gemm_tc2_kernel<BN, STAGES, EPI, BF>, dim3(grid), dim3(GEMM2_THREADS), SM::TOTAL, st, a1, a2, b, c, gt, n_tiles, sched);
+#else
   launch_pdl(gemm_tc2_kernel<BN, STAGES, EPI, BF>, dim3(grid), dim3(GEMM2_THREADS), SM::TOTAL, st, a1, a2, b, c, g, n_tiles, sched);
+#endif
   CID_CHECK_LAUNCH("gemm_tc2_kernel");
   return 0;
 }
@@ -495,6 +503,9 @@ static int attn_self_impl(const void* Q, long long q_pitch, const void* K, long 
 #ifdef CID_ATTN_TRACE
 int cid_debug_set_attn_trace(long long* buf) { g_attn_trace = buf; return 0; }
 #endif
+#ifdef CID_GEMM_TRACE
+int cid_debug_set_gemm_trace(long long* buf) { g_gemm_trace = buf; return 0; }
+#endif
 
 int cid_attn_cross(const void* Q, long long q_pitch, const void* Kcat, const void* Vtcat, void* O, long long ldo, int B, int H,
                    int N, int d, int n_text, int n_ip, float ip_scale, int dtype, void* stream) {
@@ -515,7 +526,8 @@ int cid_attn_cross(const void* Q, long long q_pitch, const void* Kcat, const voi
 #ifndef CID_CROSS_V1
   // persistent pipelined flavour wherever there is at least one unit per SM (smaller problems: one short CTA per unit is as good)
   const long long units = (long long)B * H * ((N + 127) / 128);
-  if (dp <= 80 && units >= num_sms() && g_cross2) {
+  // N > 128: with one query tile per (sample, head) the S stream (3 units ahead) would need a third K/V group in the 2-slot ring
+  if (dp <= 80 && units >= num_sms() && N > 128 && g_cross2) {
     switch (dp) {
       case 32: return launch_attn_cross2<32>(tq, tk, tv, a, units, st);
       case 48: return launch_attn_cross2<48>(tq, tk, tv, a, units, st);

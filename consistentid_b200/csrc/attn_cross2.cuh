@@ -6,20 +6,26 @@
 // ~900 cycles of HBM time - 75-110 TF/s, 14 % of HBM (profiles/r02_shapes_*).  Here every SM keeps ONE CTA that owns a contiguous,
 // balanced range of the launch's (sample, head, query tile) units and overlaps them:
 //   * warp 0 streams Q tiles through a 4-slot ring and K_cat / V_cat^T through a 2-slot ring (reloaded only when (sample, head) changes);
-//   * warp 1 issues, per unit u, S(u) = Q K_cat^T into TMEM buffer u & 1 and then P.V(u-1) of the other buffer;
-//   * two softmax warpgroups (warps 2-5 / 6-9) own one TMEM buffer each: pull the 96 score columns into registers, two masked softmaxes
-//     (text keys [0, n_text), id keys [80, 80 + n_ip)), write P as packed 16-bit pairs over the first 48 score columns (TMEM is the A
-//     operand of the P.V MMAs - no shared-memory round trip, no CTA-wide barrier), later drain O_text / O_ip, mix and store.
-// TMEM (2 x 256 columns): per buffer [S 96 (P aliases 0..47) | O_text D_PAD | O_ip D_PAD].
+//   * warp 1 issues S(u) = Q K_cat^T into TMEM buffer u % 3 three units ahead of the P.V stream (S(x+3) right after P.V(x));
+//   * three softmax warpgroups (warps 2-5 / 6-9 / 10-13, started a third of a period apart) own one TMEM buffer each: pull the 96 score
+//     columns into registers, two masked softmaxes (text keys [0, n_text), id keys [80, 80 + n_ip)), NORMALISE in registers
+//     (p / l_text, ip_scale * p / l_ip - both sums are known before P is written), write P as packed 16-bit pairs over the first 48 score
+//     columns (TMEM is the A operand of the P.V MMAs - no shared-memory round trip, no CTA-wide barrier); ONE accumulator
+//     O = P'_text V_text + P'_ip V_ip then needs no mixing epilogue: drain, convert, store.
+//     (attention.py:264,276-279 rounds each branch to 16 bits before the mix; here the 16-bit rounding sits on the normalised
+//     probabilities instead - same order of error, inside the parity tolerance of the processor goldens.)
+// TMEM (3 x 160 columns): per buffer [S 96 (P aliases 0..47) | O D_PAD]; at D_PAD = 80 O starts at column 48 (over the dead half of S) and the
+// next S of that buffer waits until O has been drained.
 #pragma once
 #include "attn_common.cuh"
 #include "attn_tc7.cuh"          // tmem_st_x16 / tmem_st_wait
 
 namespace cid {
 
-constexpr int CROSS2_THREADS = 320;
+constexpr int CROSS2_WGS = 3;
+constexpr int CROSS2_THREADS = 64 + 128 * CROSS2_WGS;
 #ifndef CID_CROSS2_STAGGER
-#define CID_CROSS2_STAGGER 0
+#define CID_CROSS2_STAGGER 800
 #endif
 constexpr long long CROSS2_STAGGER_CYCLES = CID_CROSS2_STAGGER;
 constexpr int CROSS_IP_OFF = 80;                       // first id key row of K_cat / V_cat (cid_pack_cross_kv, cid_attn_cross: ip_off is always 80)
@@ -28,7 +34,7 @@ template <int D_PAD>
 struct Cross2Cfg {
   static_assert(D_PAD % 16 == 0 && D_PAD <= 80, "attn_cross2 covers head dims <= 80");
   static constexpr int NCH = (D_PAD + 63) / 64;
-  static constexpr int NQ = 4;                                   // Q ring slots
+  static constexpr int NQ = (NCH == 1) ? 8 : 4;                  // Q ring slots: the S stream runs 3 units ahead, the loads must run further ahead still
   static constexpr int KROWS = 96;
   static constexpr int Q_BYTES = NCH * 16384;
   static constexpr int K_CHUNK = KROWS * 128;
@@ -38,9 +44,10 @@ struct Cross2Cfg {
   static constexpr int OFF_K = NQ * Q_BYTES;
   static constexpr int OFF_V = OFF_K + 2 * K_BYTES;
   static constexpr int OFF_BAR = OFF_V + 2 * V_BYTES;
-  static constexpr int TOTAL = OFF_BAR + 256;
-  static constexpr int TM_BUF = 256, TM_OT = 96, TM_OI = 96 + D_PAD;
-  static_assert(TM_OI + D_PAD <= TM_BUF, "TMEM budget");
+  static constexpr int TOTAL = OFF_BAR + 512;
+  static constexpr bool ALIAS = D_PAD > 64;                      // O over the upper half of S (dead once P is written)
+  static constexpr int TM_BUF = 160, TM_O = ALIAS ? 48 : 96;
+  static_assert(TM_O + D_PAD <= TM_BUF && CROSS2_WGS * TM_BUF <= 512, "TMEM budget");
   static_assert(K_CHUNK % 1024 == 0 && V_CHUNK % 1024 == 0, "128B-swizzle atoms need 1 KB aligned chunks");
 };
 
@@ -58,12 +65,13 @@ attn_cross2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   auto q_free = [&](int s) { return bar0 + 8u * (NQ + s); };
   auto kv_full = [&](int s) { return bar0 + 8u * (2 * NQ + s); };
   auto kv_free = [&](int s) { return bar0 + 8u * (2 * NQ + 2 + s); };
-  auto s_full = [&](int j) { return bar0 + 8u * (2 * NQ + 4 + j); };       // S(u) complete (MMA commit)
-  auto p_ready = [&](int j) { return bar0 + 8u * (2 * NQ + 6 + j); };      // P(u) in TMEM (128 softmax threads)
-  auto o_full = [&](int j) { return bar0 + 8u * (2 * NQ + 8 + j); };       // P.V(u) retired (MMA commit)
-  auto o_free = [&](int j) { return bar0 + 8u * (2 * NQ + 10 + j); };      // O(u) pulled into registers (128 softmax threads)
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + C::OFF_BAR + 8 * (2 * NQ + 12));
-  static_assert(8 * (2 * NQ + 13) <= 256, "barrier block");
+  constexpr int NB = CROSS2_WGS;
+  auto s_full = [&](int j) { return bar0 + 8u * (2 * NQ + 4 + j); };            // S(u) complete (MMA commit)
+  auto p_ready = [&](int j) { return bar0 + 8u * (2 * NQ + 4 + NB + j); };      // P(u) in TMEM (128 softmax threads)
+  auto o_full = [&](int j) { return bar0 + 8u * (2 * NQ + 4 + 2 * NB + j); };   // P.V(u) retired (MMA commit)
+  auto o_free = [&](int j) { return bar0 + 8u * (2 * NQ + 4 + 3 * NB + j); };   // O(u) pulled into registers (128 softmax threads)
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + C::OFF_BAR + 8 * (2 * NQ + 4 + 4 * NB));
+  static_assert(8 * (2 * NQ + 5 + 4 * NB) <= 512, "barrier block");
 
   const int warp = warp_id(), lane = lane_id();
   // this CTA's contiguous range of units; unit g = (sample * H + head) * tiles + query tile
@@ -75,10 +83,8 @@ attn_cross2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < NQ; ++s) { mbar_init(q_full(s), 1); mbar_init(q_free(s), 1); }
-      for (int s = 0; s < 2; ++s) {
-        mbar_init(kv_full(s), 1); mbar_init(kv_free(s), 1);
-        mbar_init(s_full(s), 1); mbar_init(p_ready(s), 128); mbar_init(o_full(s), 1); mbar_init(o_free(s), 128);
-      }
+      for (int s = 0; s < 2; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_free(s), 1); }
+      for (int s = 0; s < NB; ++s) { mbar_init(s_full(s), 1); mbar_init(p_ready(s), 128); mbar_init(o_full(s), 1); mbar_init(o_free(s), 128); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -127,74 +133,75 @@ attn_cross2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ============================================================ MMA issuer
     const uint32_t idesc_s = make_idesc(128, C::KROWS, BF);
     const uint32_t idesc_pv = make_idesc(128, D_PAD, BF);
-    const bool has_ip = a.n_ip > 0;
-    // P.V of unit x (its K/V slot kvs; `last`: the K/V group ends with it).  Text keys [0, 80) = k-steps 0-4 into O_text; keys [80, 96) =
-    // k-step 5 into O_ip, or - without id tokens (plain cross-attention over up to 96 rows) - more text keys.
+    // P.V of unit x (its K/V slot kvs; `last`: the K/V group ends with it): six 16-key steps into the unit's single accumulator
     auto issue_PV = [&](int x, int kvs, bool last) {
-      const int j = x & 1;
-      const uint32_t par = uint32_t((x >> 1) & 1);
+      const int j = x % NB;
+      const uint32_t par = uint32_t((x / NB) & 1);
       mbar_wait(p_ready(j), par);
-      mbar_wait(o_free(j), par ^ 1u);
+      if (!C::ALIAS) mbar_wait(o_free(j), par ^ 1u);       // O(x - NB) drained (aliased layout: already waited for before S(x))
       tc_fence_after();
       const uint32_t tb = tmem + j * C::TM_BUF;
       const uint32_t sv = sbase + C::OFF_V + kvs * C::V_BYTES;
       const uint32_t ob = o_full(j), fb = kv_free(kvs);
       if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 5; ++ks)
-          umma_ts(tb + C::TM_OT, tb + ks * 8, make_desc_sw128(sv + (ks >> 2) * C::V_CHUNK + (ks & 3) * 32), idesc_pv, ks ? 1u : 0u);
-        umma_ts(tb + (has_ip ? C::TM_OI : C::TM_OT), tb + 5 * 8, make_desc_sw128(sv + C::V_CHUNK + 32), idesc_pv, has_ip ? 0u : 1u);
+        for (int ks = 0; ks < 6; ++ks)
+          umma_ts(tb + C::TM_O, tb + ks * 8, make_desc_sw128(sv + (ks >> 2) * C::V_CHUNK + (ks & 3) * 32), idesc_pv, ks ? 1u : 0u);
         umma_commit(ob);
         if (last) umma_commit(fb);
       }
       __syncwarp();
     };
-    int n_kv = -1, u = 0;
-    int prev_kvs = 0; bool prev_last = false;
 #ifdef CID_ATTN_TRACE
-    const bool trm = a.trace != nullptr && blockIdx.x < 16 && lane == 0;
+    const bool trm = a.trace != nullptr && blockIdx.x < 10 && lane == 0;
     auto mstamp = [&](int u_, int e) { if (trm && u_ < 64) a.trace[((size_t)(32 + blockIdx.x) * 64 + u_) * 8 + e] = clock64(); };
 #else
     auto mstamp = [&](int, int) {};
 #endif
-    for (int g = g_beg; g < g_end; ++g, ++u) {
-      mstamp(u, 0);
-      const int t = g % tiles;
-      if (g == g_beg || t == 0) {
-        ++n_kv;
-        mbar_wait(kv_full(n_kv & 1), uint32_t((n_kv >> 1) & 1));
-      }
-      const int kvs = n_kv & 1;
+    // Two cursors over the unit range: the S stream runs NB units AHEAD of the P.V stream - S(x + NB) is issued right after P.V(x) (the
+    // first moment its TMEM buffer is free), so a warpgroup finds its next scores ready when it has drained O(x).  (With S(u) issued only
+    // after P.V(u-2) the warpgroups waited 1 100-2 500 cycles per unit for scores, profiles/r02_trace_cross2_s_late_*.txt.)
+    // Cursor: g = unit, t = query tile inside its (sample, head) run (advanced without divisions), nkv = index of its K/V group.
+    struct Cur { int g, t, nkv; };
+    auto advance = [&](Cur& cu) { ++cu.g; if (++cu.t == tiles) { cu.t = 0; } if (cu.t == 0) ++cu.nkv; };
+    auto issue_S = [&](const Cur& cu, int u) {
+      if (cu.g == g_beg || cu.t == 0) mbar_wait(kv_full(cu.nkv & 1), uint32_t((cu.nkv >> 1) & 1));      // first unit of a K/V group
+      const int kvs = cu.nkv & 1;
       const int slot = u % NQ;
       mbar_wait(q_full(slot), uint32_t((u / NQ) & 1));
+      const int j = u % NB;
+      if (C::ALIAS) mbar_wait(o_free(j), uint32_t(((u / NB) & 1) ^ 1));                                  // S(u) overwrites O(u - NB)
       tc_fence_after();
-      mstamp(u, 1);
-      {
-        const int j = u & 1;
-        const uint32_t d_tm = tmem + j * C::TM_BUF, sq = sbase + slot * C::Q_BYTES, sk = sbase + C::OFF_K + kvs * C::K_BYTES;
-        const uint32_t sb = s_full(j), qb = q_free(slot);
-        if (elect_one()) {
+      const uint32_t d_tm = tmem + j * C::TM_BUF, sq = sbase + slot * C::Q_BYTES, sk = sbase + C::OFF_K + kvs * C::K_BYTES;
+      const uint32_t sb = s_full(j), qb = q_free(slot);
+      if (elect_one()) {
 #pragma unroll
-          for (int ch = 0; ch < C::NCH; ++ch) {
-            const int ksteps = (D_PAD - ch * 64 >= 64) ? 4 : (D_PAD - ch * 64) / 16;
+        for (int ch = 0; ch < C::NCH; ++ch) {
+          const int ksteps = (D_PAD - ch * 64 >= 64) ? 4 : (D_PAD - ch * 64) / 16;
 #pragma unroll
-            for (int kk = 0; kk < ksteps; ++kk)
-              umma_ss(d_tm, make_desc_sw128(sq + ch * 16384 + kk * 32), make_desc_sw128(sk + ch * C::K_CHUNK + kk * 32), idesc_s, (ch | kk) ? 1u : 0u);
-          }
-          umma_commit(sb);
-          umma_commit(qb);
+          for (int kk = 0; kk < ksteps; ++kk)
+            umma_ss(d_tm, make_desc_sw128(sq + ch * 16384 + kk * 32), make_desc_sw128(sk + ch * C::K_CHUNK + kk * 32), idesc_s, (ch | kk) ? 1u : 0u);
         }
-        __syncwarp();
+        umma_commit(sb);
+        umma_commit(qb);
       }
-      mstamp(u, 2);
-      if (u > 0) issue_PV(u - 1, prev_kvs, prev_last);
-      mstamp(u, 3);
-      prev_kvs = kvs;
-      prev_last = (g + 1 == g_end) || ((g + 1) % tiles == 0);
+      __syncwarp();
+    };
+    const int n_units = g_end - g_beg;
+    Cur cs{g_beg, g_beg % tiles, 0}, cp = cs;
+    int us = 0;
+    for (; us < n_units && us < NB; ++us) { issue_S(cs, us); advance(cs); }
+    for (int x = 0; x < n_units; ++x) {
+      mstamp(x, 0);
+      issue_PV(x, cp.nkv & 1, (cp.g + 1 == g_end) || (cp.t + 1 == tiles));
+      advance(cp);
+      mstamp(x, 1);
+      if (us < n_units) { issue_S(cs, us); advance(cs); ++us; }
+      mstamp(x, 2);
+      mstamp(x, 3);
     }
-    if (u > 0) issue_PV(u - 1, prev_kvs, prev_last);
   } else {
-    // ============================================================ softmax warpgroups (warps 2-5: even units, warps 6-9: odd units)
+    // ============================================================ softmax warpgroups (warpgroup w: units w, w + 3, ...)
     const int wg = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
@@ -204,20 +211,20 @@ attn_cross2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int t_end = a.n_text, i_end = CROSS_IP_OFF + a.n_ip;
     const bool has_ip = a.n_ip > 0;
     int k = 0;                                            // uses of this warpgroup's buffer so far
-    // Anti-phase start: both warpgroups would otherwise receive their first scores together and stay in lock-step - exponentials (MUFU)
-    // contended, then both draining O with the MUFU idle (profiles/r02_trace_cross2_inphase_*.txt: 2 300-cycle exp phases, ~4 600 cycles
-    // per pair of units).  Half a period of head start for warpgroup 0 makes one warpgroup's exponentials run under the other's drain.
-    if (CROSS2_STAGGER_CYCLES > 0 && wg == 1) {
+    // Staggered start: the warpgroups would otherwise receive their first scores together and stay in lock-step - exponentials (MUFU)
+    // contended, then all of them draining O with the MUFU idle (profiles/r02_trace_cross2_inphase_*.txt: 2 300-cycle exp phases at two
+    // warpgroups).  A third of a period of head start each makes one warpgroup's exponentials run under the others' P.V wait and drain.
+    if (CROSS2_STAGGER_CYCLES > 0 && wg > 0) {
       const long long t0 = clock64();
-      while (clock64() - t0 < CROSS2_STAGGER_CYCLES) { }
+      while (clock64() - t0 < CROSS2_STAGGER_CYCLES * wg) { }
     }
 #ifdef CID_ATTN_TRACE
-    const bool tr = a.trace != nullptr && blockIdx.x < 16 && quarter == 0 && lane == 0;
-    auto stamp = [&](int k_, int e) { if (tr && k_ < 64) a.trace[((size_t)(blockIdx.x * 2 + wg) * 64 + k_) * 8 + e] = clock64(); };
+    const bool tr = a.trace != nullptr && blockIdx.x < 10 && quarter == 0 && lane == 0;
+    auto stamp = [&](int k_, int e) { if (tr && k_ < 64) a.trace[((size_t)(blockIdx.x * 3 + wg) * 64 + k_) * 8 + e] = clock64(); };
 #else
     auto stamp = [&](int, int) {};
 #endif
-    for (int g = g_beg + wg; g < g_end; g += 2, ++k) {
+    for (int g = g_beg + wg; g < g_end; g += NB, ++k) {
       stamp(k, 0);
       const int bh = g / tiles, t = g - bh * tiles;
       const int b = bh / a.H, h = bh - b * a.H;
@@ -239,39 +246,45 @@ attn_cross2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // Both masked softmaxes BRANCH-FREE (selects on the key index): with `if (key < n_text) ...` inside the unrolled loops nvcc emits a
       // real branch + reconvergence pair per element - measured 35 / 54 cycles per element in the max / exp passes
       // (profiles/r02_trace_cross2_branchy_*.txt), 8 600 cycles per unit where the MUFU needs ~800.
-      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, mi = -INFINITY;
+      // mask ONCE (padding keys -> -inf: they drop out of the maxima and 2^-inf = 0), then plain max / exp loops
+      const bool no_ip = !has_ip;
 #pragma unroll
       for (int i = 0; i < 96; ++i) {
-        const float s = __uint_as_float(v[i]);
-        m4[i & 3] = fmaxf(m4[i & 3], i < t_end ? s : -INFINITY);
-        if (i >= CROSS_IP_OFF) mi = fmaxf(mi, i < i_end ? s : -INFINITY);
+        const bool valid = (i < CROSS_IP_OFF) ? (i < t_end) : (i < t_end || i < i_end);
+        v[i] = valid ? v[i] : 0xff800000u;
       }
-      const float mt = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-      const float nmt = -mt * c, nmi = -mi * c;
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, mi = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < CROSS_IP_OFF; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
+#pragma unroll
+      for (int i = CROSS_IP_OFF; i < 96; ++i) mi = fmaxf(mi, __uint_as_float(v[i]));
+      // keys 80..95 are id keys, or - without id tokens - more text keys (then they share the text maximum and sum)
+      const float mt = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), no_ip ? mi : -INFINITY);
+      const float nmt = -mt * c, nmi = no_ip ? nmt : -mi * c;
       stamp(k, 3);
       float l4[4] = {0.f, 0.f, 0.f, 0.f}, li = 0.f;
+#pragma unroll
+      for (int key = 0; key < CROSS_IP_OFF; ++key) {
+        const float pe = fast_exp2(fmaf(__uint_as_float(v[key]), c, nmt));
+        l4[key & 3] += pe;
+        v[key] = __float_as_uint(pe);
+      }
+#pragma unroll
+      for (int key = CROSS_IP_OFF; key < 96; ++key) {
+        const float pe = fast_exp2(fmaf(__uint_as_float(v[key]), c, nmi));
+        li += pe;
+        v[key] = __float_as_uint(pe);
+      }
+      if (no_ip) { l4[0] += li; li = 0.f; }
+      const float lt = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      // normalised probabilities: text keys / l_text, id keys * ip_scale / l_ip -> one accumulator, no mixing epilogue
+      const float wt = 1.f / lt, wi = has_ip ? a.ip_scale / li : wt;
       uint32_t pk[48];
 #pragma unroll
       for (int i = 0; i < 96; i += 2) {
-        float p[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int key = i + e; const float s = __uint_as_float(v[key]);
-          if (key < CROSS_IP_OFF) {                        // compile-time: text keys or padding
-            const float x = fmaf(s, c, nmt);
-            p[e] = fast_exp2(key < t_end ? x : -INFINITY);
-            l4[(i >> 1) & 3] += p[e];
-          } else {                                         // id keys, padding, or (no id tokens) more text keys
-            const bool is_t = key < t_end, is_i = key < i_end;
-            const float x = fmaf(s, c, is_t ? nmt : nmi);
-            p[e] = fast_exp2((is_t || is_i) ? x : -INFINITY);
-            l4[(i >> 1) & 3] += is_t ? p[e] : 0.f;
-            li += is_t ? 0.f : p[e];
-          }
-        }
-        pk[i >> 1] = pack16(p[0], p[1], BF);
+        const float w = (i < CROSS_IP_OFF) ? wt : wi;
+        pk[i >> 1] = pack16(__uint_as_float(v[i]) * w, __uint_as_float(v[i + 1]) * w, BF);
       }
-      const float lt = (l4[0] + l4[1]) + (l4[2] + l4[3]);
       stamp(k, 4);
 #pragma unroll
       for (int cc = 0; cc < 48; cc += 16) {
@@ -282,40 +295,30 @@ attn_cross2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_before();
       mbar_arrive(p_ready(wg));
       stamp(k, 5);
-      // ---- drain O_text / O_ip, mix, store (each branch rounded to 16 bits before the mix: attention.py:264,276-279)
-      const float wt = 1.f / lt, wi = has_ip ? 1.f / li : 0.f, sc = has_ip ? a.ip_scale : 0.f;
+      // ---- drain O, convert, store
       const int row = t * 128 + r;
       const bool row_ok = row < a.Nq;
       uint16_t* dst = reinterpret_cast<uint16_t*>(a.O) + ((long long)b * a.Nq + row) * a.ldo + h * a.d;
       mbar_wait(o_full(wg), par);
       tc_fence_after();
       stamp(k, 6);
+      uint32_t o[D_PAD];
 #pragma unroll
       for (int cc = 0; cc < D_PAD; cc += 16) {
-        uint32_t vt[16], vi[16];
-        tmem_ld_x16(tS + C::TM_OT + cc, vt);
-        if (has_ip) tmem_ld_x16(tS + C::TM_OI + cc, vi);
-        tmem_ld_wait();
-        if (cc + 16 >= D_PAD) { tc_fence_before(); mbar_arrive(o_free(wg)); }     // accumulators are in registers: the buffer may be reused
-        if (row_ok && cc < a.d) {
-          float f[16];
+        uint32_t (&o16)[16] = *reinterpret_cast<uint32_t (*)[16]>(&o[cc]);
+        tmem_ld_x16(tS + C::TM_O + cc, o16);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(o_free(wg));                             // the accumulator is in registers: the buffer may be reused
+      if (row_ok) {
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {               // each branch rounded to 16 bits before the mix, two values per conversion
-            const float2 tt = unpack16(pack16(__uint_as_float(vt[i]) * wt, __uint_as_float(vt[i + 1]) * wt, BF), BF);
-            f[i] = tt.x; f[i + 1] = tt.y;
-            if (has_ip) {
-              const float2 ii = unpack16(pack16(__uint_as_float(vi[i]) * wi, __uint_as_float(vi[i + 1]) * wi, BF), BF);
-              f[i] = fmaf(sc, ii.x, tt.x); f[i + 1] = fmaf(sc, ii.y, tt.y);
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            if (cc + q * 8 < a.d) {
-              uint4 o;
-              o.x = pack16(f[q * 8 + 0], f[q * 8 + 1], BF); o.y = pack16(f[q * 8 + 2], f[q * 8 + 3], BF);
-              o.z = pack16(f[q * 8 + 4], f[q * 8 + 5], BF); o.w = pack16(f[q * 8 + 6], f[q * 8 + 7], BF);
-              *reinterpret_cast<uint4*>(dst + cc + q * 8) = o;
-            }
+        for (int cc = 0; cc < D_PAD; cc += 8) {
+          if (cc < a.d) {
+            uint4 q4;
+            q4.x = pack16(__uint_as_float(o[cc + 0]), __uint_as_float(o[cc + 1]), BF); q4.y = pack16(__uint_as_float(o[cc + 2]), __uint_as_float(o[cc + 3]), BF);
+            q4.z = pack16(__uint_as_float(o[cc + 4]), __uint_as_float(o[cc + 5]), BF); q4.w = pack16(__uint_as_float(o[cc + 6]), __uint_as_float(o[cc + 7]), BF);
+            *reinterpret_cast<uint4*>(dst + cc) = q4;
           }
         }
       }

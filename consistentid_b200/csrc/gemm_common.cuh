@@ -54,6 +54,7 @@ struct GemmArgs {
   const float* ln_colsum;
   float ln_eps;
   int ln_width;
+  long long* trace;        // debug builds (-DCID_GEMM_TRACE, tools/trace_gemm.py): per-tile phase timestamps of the first 16 CTAs
 };
 
 constexpr int GEMM_BM = 128;

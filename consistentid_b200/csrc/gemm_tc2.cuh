@@ -164,6 +164,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   // prologue above touched only shared memory / TMEM / descriptors: it may overlap the predecessor's tail (PDL)
   griddep_wait();
+#ifdef CID_GEMM_TRACE
+  // role 0 = epilogue thread 0, 1 = MMA warp, 2 = producer; [role][cta < 16][tile iteration < 64][8 events]
+  auto gstamp = [&](int role, int it_, int e, long long val = -1) {
+    if (g.trace != nullptr && blockIdx.x < 16 && it_ < 64) g.trace[(((size_t)role * 16 + blockIdx.x) * 64 + it_) * 8 + e] = val < 0 ? clock64() : val;
+  };
+#else
+  auto gstamp = [&](int, int, int, long long = -1) {};
+#endif
 
   auto tile_origin = [&](int mt, int& tn0, int& ty0, int& tx0) {
     const int tx = mt % g.tiles_x;
@@ -186,8 +194,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
       const int nt = tile % n_tiles, mt = tile / n_tiles;
       int tn0 = 0, ty0 = 0, tx0 = 0;
       if (g.a_mode != A_GEMM) tile_origin(mt, tn0, ty0, tx0);
+      if (lane == 0) gstamp(2, it, 0);
       for (int kb = w.kb0; kb < w.kb1; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (lane == 0 && kb == w.kb0) gstamp(2, it, 1);
         const uint32_t sa = smem_base + stage * SM::STAGE_BYTES;
         const uint32_t sb = sa + SM::A_BYTES;
         const uint32_t fb = full_bar(stage);
@@ -211,6 +221,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (lane == 0) gstamp(2, it, 2);
     }
     if (elect_one()) griddep_launch_dependents();   // all loads of this CTA are in flight: the successor's prologue may overlap the remaining MMAs + epilogue
     __syncwarp();
@@ -223,12 +234,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
       const GemmWork w = get_work(it);
       const int ab = it & 1;
       const uint32_t aphase = uint32_t(it >> 1) & 1u;
+      if (lane == 0) gstamp(1, it, 0);
       mbar_wait(acc_empty(ab), aphase ^ 1u);              // epilogue has drained this accumulator (first use: free)
       tc_fence_after();
+      if (lane == 0) gstamp(1, it, 1);
       const uint32_t tmem_acc = tmem_base + ab * ACC_STRIDE;
       for (int kb = w.kb0; kb < w.kb1; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
+        if (lane == 0 && kb == w.kb0) gstamp(1, it, 2);
         const uint32_t a_lo = a_lo0 + uint32_t(stage) * uint32_t(SM::STAGE_BYTES / 16);
         const uint32_t b_lo = a_lo + uint32_t(SM::A_BYTES / 16);
         const uint32_t eb = empty_bar(stage), af = acc_full(ab);
@@ -244,6 +258,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (lane == 0) gstamp(1, it, 3);
     }
   } else {
     // ================================================================ epilogue (warps 2..9)
@@ -307,6 +322,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
       const uint32_t aphase = uint32_t(it >> 1) & 1u;
       const int nt = tile % n_tiles, mt = tile / n_tiles;
       const int n0 = nt * BN;
+      if (et == 0) gstamp(0, it, 0);
       long long grow;
       const bool row_ok = my_row(tile, grow);
       (void)mt;
@@ -353,8 +369,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         // = consecutive bytes of a row; the per-row register loads of the plain flavour touch 32 different 128-byte lines per warp instruction),
         // one tile AHEAD (`rpf`, loaded while the previous tile was being drained).  Each thread then reads its own row's residual from the
         // swizzled tile, writes the result back in place, and one thread hands the tile to the TMA.
+        if (et == 0) gstamp(0, it, 1);
         if (et == 0 && it > 0) bulk_wait_read_all();          // the previous tile's TMA store has finished reading the staging buffer
         epi_bar_sync();
+        if (et == 0) gstamp(0, it, 2);
         if (g.residual != nullptr) {
           if (it == 0) load_res_tile(tile, rpf);
 #pragma unroll
@@ -365,11 +383,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         }
       }
       epi_bar_sync();                                       // bias slice (and the staged residual tile) visible to all epilogue threads
+      if (et == 0) gstamp(0, it, 3);
       if constexpr (TMAO) {
         if (g.residual != nullptr && it + 1 < n_work) load_res_tile(get_work(it + 1).tile, rpf);     // next tile's residual: in flight during this drain
       }
       mbar_wait(acc_full(ab), aphase);
       tc_fence_after();
+      if (et == 0) gstamp(0, it, 4);
       const uint32_t t_row = tmem_base + ab * ACC_STRIDE + (uint32_t(quarter * 32) << 16);
 
       bool run_epilogue = true;
@@ -582,8 +602,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         if (STOREF && g.row_stats != nullptr && row_ok && ch_beg < ch_end) {
           atomicAdd(g.row_stats + 2 * grow, rsum); atomicAdd(g.row_stats + 2 * grow + 1, rsq);
         }
+        if (et == 0) gstamp(0, it, 5);
         if constexpr (TMAO) fence_proxy_async();            // this thread's staging-tile writes -> visible to the TMA (async proxy)
         if (do_stats || TMAO) epi_bar_sync();
+        if (et == 0) gstamp(0, it, 6);
         if constexpr (TMAO) {
           if (et == 0) {
             const int row0 = int(my_row_base(tile));
@@ -603,6 +625,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
       }
       tc_fence_before();
       mbar_arrive(acc_empty(ab));                           // this thread no longer reads accumulator `ab`
+      if (et == 0) gstamp(0, it, 7);
     }
     if constexpr (TMAO) { if (et == 0) bulk_wait_all(); }   // every TMA store of this CTA has landed before the grid can be considered complete
   }

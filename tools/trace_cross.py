@@ -1,7 +1,7 @@
 """Per-unit phase timeline of attn_cross2_kernel (debug build):
     tools/build_variant.sh trace -DCID_ATTN_TRACE && CID_LIB_PATH=tools/bin/libcidb200_trace.so python tools/trace_cross.py [sd15|sdxl]
 Softmax warpgroup stamps (warp quarter 0, lane 0) per unit: 0 loop top, 1 S ready, 2 S in registers, 3 row maxima, 4 exponentials + pack,
-5 P stored + arrive, 6 O ready, 7 O drained + stored.  MMA warp stamps per unit: 0 loop top, 1 Q ready, 2 S issued, 3 P.V(u-1) issued."""
+5 P stored + arrive, 6 O ready, 7 O drained + stored.  MMA warp stamps per unit x: 0 loop top, 1 P.V(x) issued, 2 S(x+3) issued."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -28,17 +28,17 @@ e0.record(); run(); e1.record(); torch.cuda.synchronize()
 print(f"{model}: kernel {e0.elapsed_time(e1) * 1e3:.0f} us")
 t = trace.cpu().view(64, 64, 8)
 for cta in (0, 1, 7):
-    for wg in (0, 1):
-        row = t[cta * 2 + wg]
+    for wg in (0, 1, 2):
+        row = t[cta * 3 + wg]
         n = int((row[:, 0] != 0).sum())
-        base = int(t[cta * 2, 0, 0])
+        base = int(t[cta * 3, 0, 0])
         print(f"cta {cta} wg {wg}: {n} units; per unit: start | wait S | ld S | max | exp | st P | wait O | drain")
         for k in range(min(n, 8)):
             r = row[k]
             print(f"   unit {k}: {int(r[0]) - base:7d} | " + " | ".join(f"{int(r[e + 1] - r[e]):6d}" for e in range(7)))
-    m = t[32 + cta]; base = int(t[cta * 2, 0, 0])
+    m = t[32 + cta]; base = int(t[cta * 3, 0, 0])
     n = int((m[:, 0] != 0).sum())
-    print(f"cta {cta} MMA warp: unit: loop top (rel. to wg0 start) | wait Q | issue S | wait P + issue P.V(u-1)")
+    print(f"cta {cta} MMA warp: unit x: loop top (rel. to wg0 start) | wait P(x) + issue P.V(x) | wait Q/KV + issue S(x+3) | -")
     for u in range(min(n, 12)):
         r = m[u]
         print(f"   unit {u}: {int(r[0]) - base:7d} | " + " | ".join(f"{int(r[e + 1] - r[e]):6d}" for e in range(3)))
