@@ -132,6 +132,11 @@ bool g_tma_epilogue = false;      // A/B builds: register epilogue everywhere
 bool g_tma_epilogue = true;
 #endif
 int g_tma_epilogue_max_kb = 24;
+#ifdef CID_NO_TMA_EPILOGUE_DBL
+bool g_tma_epilogue_dbl = false;
+#else
+bool g_tma_epilogue_dbl = true;
+#endif
 bool g_cross2 = true;
 #ifdef CID_GEMM_TRACE
 long long* g_gemm_trace = nullptr;       // debug builds only (tools/trace_gemm.py)
@@ -171,7 +176,7 @@ int pick_tile_n(int N, int epi, int m_tiles, int num_kb, bool ws) {
 template <int BN, int STAGES, int EPI, int BF>
 int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& c, const GemmArgs& g, int grid,
                  const GemmSched& sched, int n_tiles, cudaStream_t st) {
-  using SM = Gemm2Smem<BN, STAGES, EPI == EPI_STORE_TMA>;
+  using SM = Gemm2Smem<BN, STAGES, EPI == EPI_STORE_TMA2 ? 2 : (EPI == EPI_STORE_TMA ? 1 : 0)>;
   static bool configured[MAX_DEVICES] = {};
   if (int rc = set_smem(gemm_tc2_kernel<BN, STAGES, EPI, BF>, SM::TOTAL, "gemm_tc2_kernel", configured)) return rc;
 #ifdef CID_GEMM_TRACE
@@ -184,7 +189,7 @@ int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap
   return 0;
 }
 // STAGES_T: ring depth of the TMA-store flavour (its 128 x BN staging tile comes out of the operand ring's shared memory)
-template <int BN, int STAGES, int STAGES_T>
+template <int BN, int STAGES, int STAGES_T, int STAGES_T2 = STAGES_T>
 int launch_gemm2_any(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap* c_out, const GemmArgs& g, int m_tiles,
                      void* ws, size_t ws_bytes, cudaStream_t st) {
   const int n_tiles = (g.N + BN - 1) / BN;
@@ -219,7 +224,14 @@ int launch_gemm2_any(const CUtensorMap& a1, const CUtensorMap& a2, const CUtenso
     // staging tile costs one operand-ring stage, which long K loops miss more than they gain from the coalesced stores.  Measured A/B in
     // profiles/r02_tma_epilogue_ab.txt: 8192x1280x1280 51.6 -> 44.0 us, 65536x320x320 -13 %, but 8192x1280x5120 116 -> 126 us.
     const int num_kb_all = g.taps * (g.kblocks_a1 + g.kblocks_a2);
-    if (c_out != nullptr && sched.ksplit == 1 && g_tma_epilogue && num_kb_all <= g_tma_epilogue_max_kb) return CID_G2(STAGES_T, EPI_STORE_TMA);
+    if (c_out != nullptr && sched.ksplit == 1 && g_tma_epilogue && num_kb_all <= g_tma_epilogue_max_kb) {
+      // K <= 640 with a residual: the epilogue, not the main loop, bounds the tile - two staging tiles (the residual of tile i+1 is copied a
+      // whole tile ahead) at the price of a 3-stage operand ring; longer K keeps the deeper ring and one staging tile
+      if constexpr (BN == 160 || BN == 64) {
+        if (g.residual != nullptr && num_kb_all <= 10 && g_tma_epilogue_dbl) return CID_G2(STAGES_T2, EPI_STORE_TMA2);
+      }
+      return CID_G2(STAGES_T, EPI_STORE_TMA);
+    }
   } else {
     if (flavour != EPI_STORE) return fail(CID_ERR_UNSUPPORTED, "GEGLU / QKV epilogues need an N tile >= 32");
   }
@@ -231,8 +243,8 @@ int dispatch_gemm(int bn, const CUtensorMap& a1, const CUtensorMap& a2, const CU
                   int m_tiles, void* ws, size_t ws_bytes, cudaStream_t st) {
   switch (bn) {
     case 256: return launch_gemm2_any<256, 4, 3>(a1, a2, b, c_out, g, m_tiles, ws, ws_bytes, st);
-    case 160: return launch_gemm2_any<160, 5, 4>(a1, a2, b, c_out, g, m_tiles, ws, ws_bytes, st);
-    case 64: return launch_gemm2_any<64, 8, 6>(a1, a2, b, c_out, g, m_tiles, ws, ws_bytes, st);
+    case 160: return launch_gemm2_any<160, 5, 4, 3>(a1, a2, b, c_out, g, m_tiles, ws, ws_bytes, st);
+    case 64: return launch_gemm2_any<64, 8, 6, 6>(a1, a2, b, c_out, g, m_tiles, ws, ws_bytes, st);
     case 16: return launch_gemm2_any<16, 8, 8>(a1, a2, b, nullptr, g, m_tiles, ws, ws_bytes, st);
   }
   return fail(CID_ERR_UNSUPPORTED, "no GEMM instantiation for tile N %d", bn);

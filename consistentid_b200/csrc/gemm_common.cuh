@@ -14,7 +14,7 @@
 
 namespace cid {
 
-enum EpiMode : int { EPI_STORE = 0, EPI_GEGLU = 1, EPI_QKV = 2, EPI_GELU = 3, EPI_STORE_TMA = 5 };   // EPI_STORE_TMA: kernel-internal flavour (store epilogue staged through smem + TMA)   // EPI_GELU: C = gelu_erf(acc + bias) (CLIP MLP fc1)
+enum EpiMode : int { EPI_STORE = 0, EPI_GEGLU = 1, EPI_QKV = 2, EPI_GELU = 3, EPI_STORE_TMA = 5, EPI_STORE_TMA2 = 6 };   // EPI_STORE_TMA2: the same with two staging tiles (residual prefetched a tile ahead)   // EPI_STORE_TMA: kernel-internal flavour (store epilogue staged through smem + TMA)   // EPI_GELU: C = gelu_erf(acc + bias) (CLIP MLP fc1)
 enum AMode : int { A_GEMM = 0, A_CONV = 1, A_CONV_S2 = 2 };
 
 struct GemmArgs {

@@ -33,7 +33,7 @@ constexpr int GEMM2_EPI_THREADS = GEMM2_EPI_WARPS * 32;
 constexpr int GEMM2_THREADS = 64 + GEMM2_EPI_THREADS;
 constexpr int GEMM2_PARTS = GEMM2_EPI_WARPS / 4;            // column ranges per lane quarter
 
-template <int BN, int STAGES, bool TMA_OUT = false>
+template <int BN, int STAGES, int TMA_OUT = 0>            // TMA_OUT: number of 128 x BN staging tiles of the TMA-store flavours (0, 1 or 2)
 struct Gemm2Smem {
   static constexpr int A_BYTES = GEMM_BM * 128;
   static constexpr int B_BYTES = BN * 128;
@@ -45,7 +45,8 @@ struct Gemm2Smem {
   static constexpr int CS_OFF = STAT_OFF + 2 * 2 * BN * 4;   // 2 x BN floats: column sums of the gamma-scaled weights (folded LayerNorm)
   // TMA-store flavour: the 128 x BN 16-bit output tile (and, before it, the residual tile) staged as BN/32 boxes of [128 rows x 64 B], 64B-swizzled
   static constexpr int OUT_OFF = (CS_OFF + 2 * BN * 4 + 1023) / 1024 * 1024;
-  static constexpr int OUT_BYTES = TMA_OUT ? GEMM_BM * BN * 2 : 0;
+  static constexpr int OUT_TILE = GEMM_BM * BN * 2;
+  static constexpr int OUT_BYTES = TMA_OUT * OUT_TILE;
   static constexpr int TOTAL = OUT_OFF + OUT_BYTES + 1024;
 };
 
@@ -113,11 +114,12 @@ __global__ void __launch_bounds__(GEMM2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const GemmArgs g, const int n_tiles,
                 const GemmSched sched) {
-  constexpr bool TMAO = EPI == EPI_STORE_TMA;                  // store flavour with the output (and residual) tile staged through shared memory
+  constexpr bool TMAO = EPI == EPI_STORE_TMA || EPI == EPI_STORE_TMA2;   // store flavour with the output (and residual) tile staged through shared memory
+  constexpr bool DBL = EPI == EPI_STORE_TMA2;                  // two staging tiles: tile i works in buffer i & 1, the residual of tile i+1 is copied a tile ahead
   constexpr bool STOREF = EPI == EPI_STORE || TMAO;
   static_assert(BN % 32 == 0 || BN == 16, "column split");
   constexpr int ACC_STRIDE = 256;                              // TMEM column offset between the two accumulators
-  using SM = Gemm2Smem<BN, STAGES, TMAO>;
+  using SM = Gemm2Smem<BN, STAGES, DBL ? 2 : (TMAO ? 1 : 0)>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -299,11 +301,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     };
     volatile int* last_flag = reinterpret_cast<volatile int*>(smem_gen + SM::FLAG_OFF);
     // TMA-store flavour: staging tile + the coalesced residual loader (chunk q of the tile = row q / (BN/8), 16-byte column chunk q % (BN/8))
-    uint8_t* stage_out = smem_gen + SM::OUT_OFF;
+    uint8_t* const stage_base = smem_gen + SM::OUT_OFF;
     constexpr int NPF = TMAO ? (GEMM_BM * BN / 8) / GEMM2_EPI_THREADS : 1;
     static_assert(!TMAO || (GEMM_BM * BN / 8) % GEMM2_EPI_THREADS == 0, "tile chunks must divide over the epilogue threads");
-    uint4 rpf[NPF];
-    auto load_res_tile = [&](int tile_, uint4 (&dst)[NPF]) {
+    // Residual tile -> staging tile with cp.async (LDGSTS): coalesced 16-byte chunks (consecutive threads = consecutive bytes of a row), global
+    // memory straight into the swizzled shared-memory slots, NO registers.  (The first version held the chunks in registers one tile ahead;
+    // under the 96-register cap nvcc homed them in local memory, and the spill store right behind each load waited for the data: 2 400 exposed
+    // cycles per tile plus 1 400 for the register -> shared copy, profiles/r02_trace_gemm_epilogue_before.txt.)
+    auto copy_res_tile_async = [&](int tile_, int buf) {
       const long long r0 = my_row_base(tile_);
       const int c0 = (tile_ % n_tiles) * BN;
 #pragma unroll
@@ -311,10 +316,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         const int q = et + i * GEMM2_EPI_THREADS, rr = q / (BN / 8), c16 = q - rr * (BN / 8);
         const long long gr = r0 + rr;
         const int gc = c0 + c16 * 8;
-        dst[i] = (gr < g.M && gc + 8 <= g.N) ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(g.residual) + gr * g.ldr + gc))
-                                             : make_uint4(0u, 0u, 0u, 0u);
+        const bool ok = gr < g.M && gc + 8 <= g.N;
+        const uint16_t* src = reinterpret_cast<const uint16_t*>(g.residual) + (ok ? gr * g.ldr + gc : 0);
+        const uint32_t dst = smem_base + SM::OUT_OFF + buf * SM::OUT_TILE + (c16 >> 2) * (GEMM_BM * 64) + rr * 64 + (((c16 & 3) ^ ((rr >> 1) & 3)) << 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");   // src-size 0: zero fill
       }
     };
+    if constexpr (DBL) {                                    // first tile's residual: nothing to overlap it with, exposed once per CTA
+      if (g.residual != nullptr && n_work > 0) copy_res_tile_async(get_work(0).tile, 0);
+    }
     for (int it = 0; it < n_work; ++it) {
       const GemmWork w = get_work(it);
       const int tile = w.tile;
@@ -326,13 +336,26 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
       long long grow;
       const bool row_ok = my_row(tile, grow);
       (void)mt;
+      const int ob = DBL ? (it & 1) : 0;                     // staging tile of this work item
+      uint8_t* const stage_out = stage_base + ob * SM::OUT_TILE;
+      if constexpr (DBL) { if (et == 0) { gstamp(0, it, 1); gstamp(0, it, 2); } }
+      if constexpr (TMAO && !DBL) {
+        // ---- single staging tile: once the previous tile's TMA store has finished reading it, this tile's residual is copied into it
+        // asynchronously; the copy's latency overlaps only the staging loops below (~2 400 exposed cycles per tile, r02_trace_gemm_*)
+        if (et == 0) gstamp(0, it, 1);
+        if (et == 0 && it > 0) bulk_wait_read_all();
+        epi_bar_sync();
+        if (et == 0) gstamp(0, it, 2);
+        if (g.residual != nullptr) copy_res_tile_async(tile, 0);
+      }
       // stage this tile's bias slice (fp32) in smem; buffer alternates with the accumulator
       float* bs = bias_s + ab * BN;
       for (int j = et; j < BN; j += GEMM2_EPI_THREADS) bs[j] = (g.bias && n0 + j < g.N) ? load16(g.bias, n0 + j, bf) : 0.f;
       // folded LayerNorm (consumer side): v = acc * lnA + lnB * colsum[c] + bias[c] with lnA = rstd_r, lnB = -rstd_r mean_r (1, 0 when off)
       float* cs = cs_s + ab * BN;
       float lnA = 1.f, lnB = 0.f;
-      if (g.ln_stats != nullptr) {
+      const bool has_ln = g.ln_stats != nullptr;
+      if (has_ln) {
         for (int j = et; j < BN; j += GEMM2_EPI_THREADS) cs[j] = (n0 + j < g.N) ? g.ln_colsum[n0 + j] : 0.f;
         if (row_ok) {
           const float2 st2 = *reinterpret_cast<const float2*>(g.ln_stats + 2 * grow);
@@ -365,34 +388,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
           }
         }
       } else {
-        // ---- TMA-store flavour.  The residual tile is staged into the output staging buffer with COALESCED 16-byte loads (consecutive threads
-        // = consecutive bytes of a row; the per-row register loads of the plain flavour touch 32 different 128-byte lines per warp instruction),
-        // one tile AHEAD (`rpf`, loaded while the previous tile was being drained).  Each thread then reads its own row's residual from the
-        // swizzled tile, writes the result back in place, and one thread hands the tile to the TMA.
-        if (et == 0) gstamp(0, it, 1);
-        if (et == 0 && it > 0) bulk_wait_read_all();          // the previous tile's TMA store has finished reading the staging buffer
-        epi_bar_sync();
-        if (et == 0) gstamp(0, it, 2);
-        if (g.residual != nullptr) {
-          if (it == 0) load_res_tile(tile, rpf);
-#pragma unroll
-          for (int i = 0; i < NPF; ++i) {
-            const int q = et + i * GEMM2_EPI_THREADS, rr = q / (BN / 8), c16 = q - rr * (BN / 8);
-            *reinterpret_cast<uint4*>(stage_out + (c16 >> 2) * (GEMM_BM * 64) + rr * 64 + (((c16 & 3) ^ ((rr >> 1) & 3)) << 4)) = rpf[i];
-          }
-        }
+        if (g.residual != nullptr) asm volatile("cp.async.wait_all;" ::: "memory");      // this thread's residual chunks (of THIS tile) have landed
+        if constexpr (DBL) { if (et == 0 && it > 0) bulk_wait_read_all(); }             // the other staging tile: tile it-1's TMA store has read it
       }
       epi_bar_sync();                                       // bias slice (and the staged residual tile) visible to all epilogue threads
-      if (et == 0) gstamp(0, it, 3);
-      if constexpr (TMAO) {
-        if (g.residual != nullptr && it + 1 < n_work) load_res_tile(get_work(it + 1).tile, rpf);     // next tile's residual: in flight during this drain
+      if constexpr (DBL) {
+        // two staging tiles: the NEXT tile's residual goes into the other one now - a whole tile ahead of its use, nothing exposed
+        if (g.residual != nullptr && it + 1 < n_work) copy_res_tile_async(get_work(it + 1).tile, ob ^ 1);
       }
+      if (et == 0) gstamp(0, it, 3);
       mbar_wait(acc_full(ab), aphase);
       tc_fence_after();
       if (et == 0) gstamp(0, it, 4);
       const uint32_t t_row = tmem_base + ab * ACC_STRIDE + (uint32_t(quarter * 32) << 16);
 
       bool run_epilogue = true;
+      bool released = false;                               // acc_empty already signalled for this tile
       if (w.split >= 0) {
         // ---- split-K tail unit: publish the partial accumulator; the last arriver of the tile folds the others in and finishes
         constexpr int SLOT = GEMM_BM * BN;                                  // floats per partial
@@ -472,12 +483,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             if (row_ok) {
               uint32_t packed[8];
 #pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                const float v0 = fmaf(__uint_as_float(a[j]), lnA, fmaf(lnB, cs[ch * 16 + j], bs[ch * 16 + j]));
-                const float v1 = fmaf(__uint_as_float(a[j + 1]), lnA, fmaf(lnB, cs[ch * 16 + j + 1], bs[ch * 16 + j + 1]));
-                const float g0 = fmaf(__uint_as_float(b[j]), lnA, fmaf(lnB, cs[HALF + ch * 16 + j], bs[HALF + ch * 16 + j]));
-                const float g1 = fmaf(__uint_as_float(b[j + 1]), lnA, fmaf(lnB, cs[HALF + ch * 16 + j + 1], bs[HALF + ch * 16 + j + 1]));
-                packed[j >> 1] = pack16(v0 * gelu_erf(g0), v1 * gelu_erf(g1), bf);
+              for (int q = 0; q < 4; ++q) {                // 16-byte reads of the bias / column-sum slices (value and gate halves)
+                const float4 bv = *reinterpret_cast<const float4*>(bs + ch * 16 + q * 4), bg = *reinterpret_cast<const float4*>(bs + HALF + ch * 16 + q * 4);
+                const float4 cv = *reinterpret_cast<const float4*>(cs + ch * 16 + q * 4), cg = *reinterpret_cast<const float4*>(cs + HALF + ch * 16 + q * 4);
+                const int j = q * 4;
+                const float v0 = fmaf(__uint_as_float(a[j]), lnA, fmaf(lnB, cv.x, bv.x)), v1 = fmaf(__uint_as_float(a[j + 1]), lnA, fmaf(lnB, cv.y, bv.y));
+                const float v2 = fmaf(__uint_as_float(a[j + 2]), lnA, fmaf(lnB, cv.z, bv.z)), v3 = fmaf(__uint_as_float(a[j + 3]), lnA, fmaf(lnB, cv.w, bv.w));
+                const float g0 = fmaf(__uint_as_float(b[j]), lnA, fmaf(lnB, cg.x, bg.x)), g1 = fmaf(__uint_as_float(b[j + 1]), lnA, fmaf(lnB, cg.y, bg.y));
+                const float g2 = fmaf(__uint_as_float(b[j + 2]), lnA, fmaf(lnB, cg.z, bg.z)), g3 = fmaf(__uint_as_float(b[j + 3]), lnA, fmaf(lnB, cg.w, bg.w));
+                packed[q * 2] = pack16(v0 * gelu_erf(g0), v1 * gelu_erf(g1), bf);
+                packed[q * 2 + 1] = pack16(v2 * gelu_erf(g2), v3 * gelu_erf(g3), bf);
               }
               uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(g.C) + grow * g.ldc + out_col0 + ch * 16);
               dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -505,8 +520,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             const bool active = row_ok && col0 < g.N;
             float v[16];
             if (active) {
+              // bias (and, with a folded LayerNorm, column-sum) slices as 16-byte shared-memory reads: the scalar form issued 32 LDS per
+              // chunk and thread - 1 280 warp-level LDS per 128x160 tile on the single LSU, about half of the drain (r02_trace_gemm_*)
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(a[j]), lnA, fmaf(lnB, cs[ch * 16 + j], bs[ch * 16 + j]));
+              for (int q = 0; q < 4; ++q) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bs + ch * 16 + q * 4);
+                v[q * 4 + 0] = b4.x; v[q * 4 + 1] = b4.y; v[q * 4 + 2] = b4.z; v[q * 4 + 3] = b4.w;
+              }
+              if (has_ln) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 c4 = *reinterpret_cast<const float4*>(cs + ch * 16 + q * 4);
+                  v[q * 4 + 0] = fmaf(lnB, c4.x, v[q * 4 + 0]); v[q * 4 + 1] = fmaf(lnB, c4.y, v[q * 4 + 1]);
+                  v[q * 4 + 2] = fmaf(lnB, c4.z, v[q * 4 + 2]); v[q * 4 + 3] = fmaf(lnB, c4.w, v[q * 4 + 3]);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(a[j]), lnA, v[j]);
               if (g.rowbias) {
                 const uint16_t* rb = reinterpret_cast<const uint16_t*>(g.rowbias) + (grow / g.rows_per_group) * g.ld_rowbias + col0;
                 if (full && ((reinterpret_cast<uintptr_t>(rb) & 15) == 0)) {
@@ -599,6 +629,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             }
           }
         }
+        // this thread's accumulator reads are complete: hand the TMEM buffer back NOW (the issuer can start tile it+2 while the statistics,
+        // the final barrier and the TMA store of this tile are still under way; thread 0's TMA issue alone cost ~800 cycles of that)
+        tc_fence_before();
+        mbar_arrive(acc_empty(ab));
+        released = true;
         if (STOREF && g.row_stats != nullptr && row_ok && ch_beg < ch_end) {
           atomicAdd(g.row_stats + 2 * grow, rsum); atomicAdd(g.row_stats + 2 * grow + 1, rsq);
         }
@@ -611,7 +646,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             const int row0 = int(my_row_base(tile));
 #pragma unroll
             for (int bx = 0; bx < BN / 32; ++bx)
-              if (n0 + bx * 32 < g.N) tma_store_2d(&tmC, smem_base + SM::OUT_OFF + bx * (GEMM_BM * 64), n0 + bx * 32, row0);
+              if (n0 + bx * 32 < g.N) tma_store_2d(&tmC, smem_base + SM::OUT_OFF + ob * SM::OUT_TILE + bx * (GEMM_BM * 64), n0 + bx * 32, row0);
             bulk_commit();
           }
         }
@@ -623,8 +658,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             if (n0 + j < g.N) { atomicAdd(dst + 2 * j, st[j]); atomicAdd(dst + 2 * j + 1, st[BN + j]); }
         }
       }
-      tc_fence_before();
-      mbar_arrive(acc_empty(ab));                           // this thread no longer reads accumulator `ab`
+      if (!released) {
+        tc_fence_before();
+        mbar_arrive(acc_empty(ab));                         // this thread no longer reads accumulator `ab`
+      }
       if (et == 0) gstamp(0, it, 7);
     }
     if constexpr (TMAO) { if (et == 0) bulk_wait_all(); }   // every TMA store of this CTA has landed before the grid can be considered complete
