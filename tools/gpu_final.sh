@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 KREG='regex:gemm_tc2|attn_|gn_|layernorm|upsample|phase_split|cfg_sched|skinny|pack_cross|latents_to|advance_step|timestep_embed|nchw|rows_to'
 timeout 1800 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/pytest_gpu_final.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu_final.log; tail -3 gpurun_out/pytest_gpu_final.log
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_final.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke_final.log
-timeout 1500 python bench.py --steps ${BENCH_STEPS:-10} --warmup 3 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "bench rc=$?"
+timeout 1500 python bench.py --steps ${BENCH_STEPS:-6} --warmup 3 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "bench rc=$?"
 timeout 600 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/bench_reference_final.json 2> gpurun_out/bench_reference_final.err; echo "ref rc=$?"
 M="gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"
 for wl in sd15 sdxl; do
@@ -25,5 +25,7 @@ cap attn7_sdxl attn_self7 sdxl attn_self
 cap conv_sd15 gemm_tc2 sd15 conv3x3
 cap ff1_sdxl gemm_tc2 sdxl gemm_ff1
 cap outproj_sd15 gemm_tc2 sd15 gemm_out_proj
+cap cross2_sd15 attn_cross2 sd15 attn_cross
+cap cross2_sdxl attn_cross2 sdxl attn_cross
 du -sh gpurun_out
 tail -c 400 gpurun_out/bench_final.json
