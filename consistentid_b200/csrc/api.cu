@@ -614,6 +614,27 @@ int cid_gn_apply_ch(const void* x1, int C1, const float* sums1, const void* x2, 
   CID_CHECK_LAUNCH("gn_apply_ch_kernel");
   return 0;
 }
+int cid_gn_small(const void* x1, int C1, const void* x2, int C2, int NB, int HW, int groups, const void* gamma, const void* beta, float eps,
+                 int silu, void* y, int dtype, void* stream) {
+  const int C = C1 + C2;
+  if (!x1 || !gamma || !beta || !y || groups <= 0 || C % groups || (C2 > 0 && !x2)) return fail(CID_ERR_ARG, "cid_gn_small: bad arguments");
+  const int cpg = C / groups;
+  if (cpg % 8 || C1 % cpg || (long long)HW * (cpg / 8) > 8LL * GN_SMALL_THREADS)
+    return fail(CID_ERR_UNSUPPORTED, "cid_gn_small: needs 8 | C/groups (%d), groups aligned with the concat boundary (C1=%d) and HW*C/groups <= %d elements",
+                cpg, C1, 64 * GN_SMALL_THREADS);
+  const int total = HW * (cpg / 8);
+  const dim3 grid(groups, NB);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CID_GNS(V) launch_pdl(gn_small_kernel<V>, grid, dim3(GN_SMALL_THREADS), 0, st, (const uint16_t*)x1, C1, (const uint16_t*)x2, C2, HW, groups, \
+                              (const uint16_t*)gamma, (const uint16_t*)beta, eps, silu, (uint16_t*)y, int(dtype == CID_BF16))
+  if (total <= GN_SMALL_THREADS) CID_GNS(1);
+  else if (total <= 2 * GN_SMALL_THREADS) CID_GNS(2);
+  else if (total <= 4 * GN_SMALL_THREADS) CID_GNS(4);
+  else CID_GNS(8);
+#undef CID_GNS
+  CID_CHECK_LAUNCH("gn_small_kernel");
+  return 0;
+}
 int cid_layernorm(const void* x, const void* gamma, const void* beta, void* y, long long rows, int C, float eps, int dtype, void* stream) {
   if (!x || !gamma || !beta || !y || C % 8 || C > 2048) return fail(CID_ERR_ARG, "cid_layernorm: C=%d must be a multiple of 8 and <= 2048", C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);

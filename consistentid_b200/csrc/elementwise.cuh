@@ -195,6 +195,80 @@ gn_apply_ch_kernel(const uint16_t* __restrict__ x1, int C1, const float* __restr
   gn_stream(x1n, C1, x2n, C2, yn, aff, per_sample, do_silu, bf);
 }
 
+// ------------------------------------------------------------------------------------------------ GroupNorm, small tensors: ONE pass
+// One CTA per (sample, group): its HW x (C / groups) slab (5-40 KB at the 8x8 / 16x16 levels) is loaded once into registers (up to VPT
+// 16-byte vectors per thread), mean and variance (two-pass over the registers, fp32) reduced across the block, affine + SiLU applied, stored.
+// Replaces gn_stats + gn_apply where the statistics cannot ride on the producer's epilogue (a 128-row tile spans two samples at HW = 64):
+// two launches of ~20 us each - block prologues and a grid-wide dependency for 2.6 MB of data - become one short launch.
+// Needs groups that do not straddle the concat boundary and 8-channel vectors that do not straddle groups (host-checked).
+constexpr int GN_SMALL_THREADS = 512;
+template <int VPT>
+__global__ void __launch_bounds__(GN_SMALL_THREADS)
+gn_small_kernel(const uint16_t* __restrict__ x1, int C1, const uint16_t* __restrict__ x2, int C2, int HW, int groups,
+                const uint16_t* __restrict__ gamma, const uint16_t* __restrict__ beta, float eps, int do_silu, uint16_t* __restrict__ y, int bf) {
+  griddep_wait();
+  __shared__ float red[2][GN_SMALL_THREADS / 32];
+  const int C = C1 + C2, cpg = C / groups, vpp = cpg / 8;              // vectors per pixel inside the group
+  const int n = blockIdx.y, gi = blockIdx.x, c0 = gi * cpg;
+  const int total = HW * vpp;
+  const bool first = c0 < C1;
+  const uint16_t* src = first ? x1 + (size_t)n * HW * C1 + c0 : x2 + (size_t)n * HW * C2 + (c0 - C1);
+  const int pitch = first ? C1 : C2;
+  float f[VPT][8];
+  int pix[VPT], vec[VPT];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const int idx = threadIdx.x + j * GN_SMALL_THREADS;
+    pix[j] = idx / vpp; vec[j] = idx - pix[j] * vpp;
+    if (idx < total) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(src + (size_t)pix[j] * pitch + vec[j] * 8)), f[j], bf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += f[j][e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[j][e] = 0.f;
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto block_sum = [&](float v, int slot) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[slot][warp] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < GN_SMALL_THREADS / 32; ++w) t += red[slot][w];
+    return t;
+  };
+  const float inv_n = 1.f / (float(HW) * float(cpg));
+  const float mean = block_sum(s, 0) * inv_n;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    if (threadIdx.x + j * GN_SMALL_THREADS < total) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = f[j][e] - mean; q = fmaf(d, d, q); }
+    }
+  }
+  const float rstd = rsqrtf(block_sum(q, 1) * inv_n + eps);
+  uint16_t* yn = y + (size_t)n * HW * C + c0;
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    if (threadIdx.x + j * GN_SMALL_THREADS < total) {
+      float g8[8], b8[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + c0 + vec[j] * 8)), g8, bf);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(beta + c0 + vec[j] * 8)), b8, bf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float v = fmaf((f[j][e] - mean) * rstd, g8[e], b8[e]);
+        f[j][e] = do_silu ? silu_f(v) : v;
+      }
+      *reinterpret_cast<uint4*>(yn + (size_t)pix[j] * C + vec[j] * 8) = pack8(f[j], bf);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm
 // LPR lanes share a row (8 / 16 / 32 for C <= 320 / 640 / 2048), i.e. a warp normalises 32 / LPR rows at once and every lane has up to VPL
 // independent 16-byte loads in flight (5 for the UNet widths 320 / 640 / 1280) - the one-row-per-warp first version had at most two and ran

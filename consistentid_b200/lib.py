@@ -44,6 +44,7 @@ _SIGS = {
     "cid_gn_stats": ([_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp], _i),
     "cid_gn_apply": ([_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _f, _i, _vp, _vp, _i, _vp], _i),
     "cid_gn_apply_ch": ([_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _f, _i, _vp, _i, _vp], _i),
+    "cid_gn_small": ([_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _i, _vp], _i),
     "cid_layernorm": ([_vp, _vp, _vp, _vp, _ll, _i, _f, _i, _vp], _i),
     "cid_upsample2x": ([_vp, _vp, _i, _i, _i, _i, _vp], _i),
     "cid_phase_split": ([_vp, _vp, _i, _i, _i, _i, _vp], _i),

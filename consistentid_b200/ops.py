@@ -162,6 +162,25 @@ def gn_apply_ch(x1, C1, sums1, x2, C2, sums2, NB, HW, groups, gamma, beta, eps, 
     return out
 
 
+GN_SMALL_MAX_ELEMS = 32768          # HW * C/groups a CTA of cid_gn_small holds in registers
+
+
+def gn_small_ok(C1, C2, HW, groups):
+    """True when cid_gn_small applies: 8-channel vectors inside groups, groups inside one source of the virtual concat, slab small enough."""
+    C = C1 + C2
+    if C % groups:
+        return False
+    cpg = C // groups
+    return cpg % 8 == 0 and C1 % cpg == 0 and HW * cpg <= GN_SMALL_MAX_ELEMS
+
+
+def gn_small(x1, C1, x2, C2, NB, HW, groups, gamma, beta, eps, silu, out):
+    """One-pass GroupNorm(+SiLU) of a small tensor (statistics and apply in one launch)."""
+    with _prof("gn_apply", 0.0, 4.0 * NB * HW * (C1 + C2), (NB * HW, C1 + C2)):
+        call("cid_gn_small", _p(x1), C1, _p(x2), C2, NB, HW, groups, _p(gamma), _p(beta), float(eps), 1 if silu else 0, _p(out), _dt(x1), _stream())
+    return out
+
+
 def layernorm(x, gamma, beta, out, rows, C, eps=1e-5):
     with _prof("layernorm", 0.0, 4.0 * rows * C, (rows, C)):
         call("cid_layernorm", _p(x), _p(gamma), _p(beta), _p(out), rows, C, float(eps), _dt(x), _stream())

@@ -94,6 +94,11 @@ int cid_gn_apply(const void* x1, int C1, const void* x2, int C2, int NB, int HW,
  * x1, sums2[NB, C2, 2] for x2 (NULL when C2 == 0).  Group statistics are formed on the fly (the 32 groups do not align with the concat boundary). */
 int cid_gn_apply_ch(const void* x1, int C1, const float* sums1, const void* x2, int C2, const float* sums2, int NB, int HW, int groups,
                     const void* gamma, const void* beta, float eps, int silu, void* y, int dtype, void* stream);
+/* GroupNorm(+SiLU) of small tensors in ONE pass (one CTA per (sample, group), the slab held in registers): for tensors whose statistics cannot
+ * ride on the producer's epilogue (HW not a multiple of 128: the 8x8 level).  Requires 8 | C/groups, C1 a multiple of C/groups and
+ * HW * C/groups <= 32768 elements; CID_ERR_UNSUPPORTED otherwise (use cid_gn_stats + cid_gn_apply). */
+int cid_gn_small(const void* x1, int C1, const void* x2, int C2, int NB, int HW, int groups, const void* gamma, const void* beta, float eps,
+                 int silu, void* y, int dtype, void* stream);
 int cid_layernorm(const void* x, const void* gamma, const void* beta, void* y, long long rows, int C, float eps, int dtype, void* stream);
 int cid_upsample2x(const void* x, void* y, int NB, int H, int W, int C, void* stream);
 int cid_phase_split(const void* x, void* y, int NB, int H, int W, int C, void* stream);

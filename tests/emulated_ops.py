@@ -157,6 +157,24 @@ def gn_apply_ch(x1, C1, sums1, x2, C2, sums2, NB, HW, groups, gamma, beta, eps, 
     return gn_apply(x1, C1, x2, C2, NB, HW, groups, sums, gamma, beta, eps, silu, out)
 
 
+def gn_small_ok(C1, C2, HW, groups):
+    C = C1 + C2
+    cpg = C // groups
+    return C % groups == 0 and cpg % 8 == 0 and C1 % cpg == 0 and HW * cpg <= 32768
+
+
+def gn_small(x1, C1, x2, C2, NB, HW, groups, gamma, beta, eps, silu, out):
+    assert gn_small_ok(C1, C2, HW, groups)
+    x = x1.float().reshape(NB, HW, C1)
+    if C2:
+        x = torch.cat([x, x2.float().reshape(NB, HW, C2)], -1)
+    yv = F.group_norm(x.permute(0, 2, 1), groups, gamma.float(), beta.float(), eps)
+    if silu:
+        yv = F.silu(yv)
+    out.copy_(yv.permute(0, 2, 1).reshape(out.shape))
+    return out
+
+
 def layernorm(x, gamma, beta, out, rows, C, eps=1e-5):
     out.copy_(F.layer_norm(x.float().reshape(rows, C), (C,), gamma.float(), beta.float(), eps).reshape(out.shape))
     return out
@@ -279,7 +297,7 @@ def ensure_workspace(device=None):
     return None
 
 
-_NAMES = ("gemm conv3x3 attn_self pack_cross_kv attn_cross gn_stats gn_apply gn_apply_ch layernorm layernorm_rows upsample2x phase_split nchw_to_nhwc_pad "
+_NAMES = ("gemm conv3x3 attn_self pack_cross_kv attn_cross gn_stats gn_apply gn_apply_ch gn_small gn_small_ok layernorm layernorm_rows upsample2x phase_split nchw_to_nhwc_pad "
           "rows_to_nchw add_inplace silu_inplace timestep_embed skinny_linear softmax_rows perceiver_attn cfg_sched_step latents_to_input "
           "advance_step inpaint_blend ensure_workspace").split()
 

@@ -308,6 +308,24 @@ def check_groupnorm(NB=2, HW=256, C1=320, C2=0, groups=32, silu=True, dtype=torc
     return _report(f"groupnorm NB{NB} HW{HW} C{C1}+{C2} silu{int(silu)} {str(dtype)[6:]}", out.reshape(-1, C), ref.reshape(-1, C), 5e-3)
 
 
+def check_gn_small(NB=3, HW=64, C1=1280, C2=0, groups=32, silu=True, dtype=torch.float16, eps=1e-5, seed=0):
+    """One-pass small-tensor GroupNorm (cid_gn_small): one CTA per (sample, group)."""
+    ops = _ops()
+    assert ops.gn_small_ok(C1, C2, HW, groups)
+    x1 = _rand((NB, HW, C1), dtype, seed) * 2 + 0.5
+    x2 = (_rand((NB, HW, C2), dtype, seed + 1) * 3 - 0.3) if C2 else None
+    C = C1 + C2
+    ga, be = _rand((C,), dtype, seed + 2) + 1, _rand((C,), dtype, seed + 3)
+    out = torch.full((NB, HW, C), float("nan"), dtype=dtype, device=DEV)
+    ops.gn_small(x1, C1, x2, C2, NB, HW, groups, ga, be, eps, silu, out)
+    torch.cuda.synchronize()
+    x = x1.float() if x2 is None else torch.cat([x1.float(), x2.float()], -1)
+    ref = F.group_norm(x.permute(0, 2, 1), groups, ga.float(), be.float(), eps)
+    if silu: ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1)
+    return _report(f"gn_small NB{NB} HW{HW} C{C1}+{C2} silu{int(silu)} {str(dtype)[6:]}", out.reshape(-1, C), ref.reshape(-1, C), 5e-3)
+
+
 def check_groupnorm_chain(NB=3, HW=256, C=320, groups=32, n=5, dtype=torch.float16, eps=1e-5, seed=0):
     """Alternating statistics buffers: only the first GroupNorm memsets, each apply zeroes the next one's buffer (unet._groupnorm)."""
     ops = _ops()
@@ -556,6 +574,12 @@ CHECKS = {
     "gemm_ln_fold": (check_gemm_layernorm_fold, dict(M=512, C=320, N=960)),
     "gemm_ln_fold_1280": (check_gemm_layernorm_fold, dict(M=384, C=1280, N=1280, dtype=B16)),
     "gemm_ln_fold_geglu": (check_gemm_layernorm_fold, dict(M=256, C=640, N=5120, epi="geglu")),
+    "gn_small_8x8_1280": (check_gn_small, dict(NB=16, HW=64, C1=1280)),
+    "gn_small_8x8_concat": (check_gn_small, dict(NB=4, HW=64, C1=1280, C2=1280, dtype=B16)),
+    "gn_small_16x16_1280": (check_gn_small, dict(NB=2, HW=256, C1=1280, silu=False)),
+    "gn_small_16x16_concat": (check_gn_small, dict(NB=2, HW=256, C1=1280, C2=1280)),
+    "gn_small_tiny": (check_gn_small, dict(NB=2, HW=16, C1=256, C2=256, groups=32)),
+    "gn_small_odd_hw": (check_gn_small, dict(NB=3, HW=36, C1=320, dtype=B16, groups=8)),
     "gn_320": (check_groupnorm, dict(C1=320)),
     "gn_concat": (check_groupnorm, dict(C1=640, C2=320, HW=1024)),
     "gn_2560": (check_groupnorm, dict(C1=1280, C2=1280, HW=64, NB=3, dtype=B16)),
