@@ -173,17 +173,17 @@ int pick_tile_n(int N, int epi, int m_tiles, int num_kb, bool ws) {
   return fixed;
 }
 
-template <int BN, int STAGES, int EPI, int BF>
+template <int BN, int STAGES, int EPI, int BF, bool LEAN = false>
 int launch_gemm2(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& c, const GemmArgs& g, int grid,
                  const GemmSched& sched, int n_tiles, cudaStream_t st) {
   using SM = Gemm2Smem<BN, STAGES, EPI == EPI_STORE_TMA2 ? 2 : (EPI == EPI_STORE_TMA ? 1 : 0)>;
   static bool configured[MAX_DEVICES] = {};
-  if (int rc = set_smem(gemm_tc2_kernel<BN, STAGES, EPI, BF>, SM::TOTAL, "gemm_tc2_kernel", configured)) return rc;
+  if (int rc = set_smem(gemm_tc2_kernel<BN, STAGES, EPI, BF, LEAN>, SM::TOTAL, "gemm_tc2_kernel", configured)) return rc;
 #ifdef CID_GEMM_TRACE
   GemmArgs gt = g; gt.trace = g_gemm_trace;
-  launch_pdl(gemm_tc2_kernel<BN, STAGES, EPI, BF>, dim3(grid), dim3(GEMM2_THREADS), SM::TOTAL, st, a1, a2, b, c, gt, n_tiles, sched);
+  launch_pdl(gemm_tc2_kernel<BN, STAGES, EPI, BF, LEAN>, dim3(grid), dim3(GEMM2_THREADS), SM::TOTAL, st, a1, a2, b, c, gt, n_tiles, sched);
 #else
-  launch_pdl(gemm_tc2_kernel<BN, STAGES, EPI, BF>, dim3(grid), dim3(GEMM2_THREADS), SM::TOTAL, st, a1, a2, b, c, g, n_tiles, sched);
+  launch_pdl(gemm_tc2_kernel<BN, STAGES, EPI, BF, LEAN>, dim3(grid), dim3(GEMM2_THREADS), SM::TOTAL, st, a1, a2, b, c, g, n_tiles, sched);
 #endif
   CID_CHECK_LAUNCH("gemm_tc2_kernel");
   return 0;
@@ -227,10 +227,19 @@ int launch_gemm2_any(const CUtensorMap& a1, const CUtensorMap& a2, const CUtenso
     if (c_out != nullptr && sched.ksplit == 1 && g_tma_epilogue && num_kb_all <= g_tma_epilogue_max_kb) {
       // K <= 640 with a residual: the epilogue, not the main loop, bounds the tile - two staging tiles (the residual of tile i+1 is copied a
       // whole tile ahead) at the price of a 3-stage operand ring; longer K keeps the deeper ring and one staging tile
+      // lean instances (no row bias / GroupNorm statistics / GELU compiled in) for the calls that use none of them: the transformer GEMMs
+#ifndef CID_NO_LEAN_EPILOGUE
+      const bool lean = g.rowbias == nullptr && g.chan_stats == nullptr && g.epi != EPI_GELU;
+#else
+      const bool lean = false;
+#endif
+#define CID_G2L(S, E) (g.is_bf16 ? launch_gemm2<BN, S, E, 1, true>(a1, a2, b, *c_out, g, grid, sched, n_tiles, st) \
+                                 : launch_gemm2<BN, S, E, 0, true>(a1, a2, b, *c_out, g, grid, sched, n_tiles, st))
       if constexpr (BN == 160 || BN == 64) {
-        if (g.residual != nullptr && num_kb_all <= 10 && g_tma_epilogue_dbl) return CID_G2(STAGES_T2, EPI_STORE_TMA2);
+        if (g.residual != nullptr && num_kb_all <= 10 && g_tma_epilogue_dbl) return lean ? CID_G2L(STAGES_T2, EPI_STORE_TMA2) : CID_G2(STAGES_T2, EPI_STORE_TMA2);
       }
-      return CID_G2(STAGES_T, EPI_STORE_TMA);
+      return lean ? CID_G2L(STAGES_T, EPI_STORE_TMA) : CID_G2(STAGES_T, EPI_STORE_TMA);
+#undef CID_G2L
     }
   } else {
     if (flavour != EPI_STORE) return fail(CID_ERR_UNSUPPORTED, "GEGLU / QKV epilogues need an N tile >= 32");

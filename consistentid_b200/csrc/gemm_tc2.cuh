@@ -109,7 +109,11 @@ struct GemmWork { int tile, kb0, kb1, split, tail_idx; };
 // EPI (epilogue flavour: EPI_STORE covers the plain / GELU / fused-statistics stores, EPI_GEGLU, EPI_QKV) and BF (0 fp16, 1 bf16) are
 // compile-time: the generic kernel was 41 k SASS instructions at BN = 256 (every flavour x both 16-bit types, fully unrolled) and ncu showed
 // instruction-fetch stalls (`no_instruction` 2.0-3.5 per issue) on the epilogue-bound GEMMs; a specialised instance holds only its own path.
-template <int BN, int STAGES, int EPI, int BF>
+// LEAN (TMA-store flavours): the epilogue is compiled WITHOUT the per-sample row bias, the fused GroupNorm statistics and the GELU - the profile of
+// the transformer GEMMs (bias, residual, output scale, LayerNorm row statistics / folded LayerNorm).  With every optional feature compiled in, a
+// 16-column chunk of the drain was ~1 000 SASS instructions, much of it if-converted (executed, then discarded by FSEL): ~2 500 cycles of
+// drain per 128x160 tile on the K = C GEMMs whose epilogue is their critical path (profiles/r02_trace_gemm_epilogue_dbl.txt).
+template <int BN, int STAGES, int EPI, int BF, bool LEAN = false>
 __global__ void __launch_bounds__(GEMM2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const GemmArgs g, const int n_tiles,
@@ -368,7 +372,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         for (int j = et; j < BN; j += GEMM2_EPI_THREADS) cs[j] = 0.f;
       }
       float rsum = 0.f, rsq = 0.f;                           // producer side: this thread's share of its row's LayerNorm statistics
-      const bool do_stats = STOREF && g.chan_stats != nullptr;
+      const bool do_stats = !LEAN && STOREF && g.chan_stats != nullptr;
       float* st = stat_s + ab * 2 * BN;
       if (do_stats) for (int j = et; j < 2 * BN; j += GEMM2_EPI_THREADS) st[j] = 0.f;
       // prefetch residual rows for this thread's chunks (latency overlaps the wait for the accumulator; prefetching a whole
@@ -537,7 +541,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
               }
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(a[j]), lnA, v[j]);
-              if (g.rowbias) {
+              if (!LEAN && g.rowbias) {
                 const uint16_t* rb = reinterpret_cast<const uint16_t*>(g.rowbias) + (grow / g.rows_per_group) * g.ld_rowbias + col0;
                 if (full && ((reinterpret_cast<uintptr_t>(rb) & 15) == 0)) {
                   float f0[8], f1[8];
@@ -587,7 +591,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] *= g.out_scale;
                 }
-                if (STOREF && g.epi == EPI_GELU) {
+                if (!LEAN && STOREF && g.epi == EPI_GELU) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
                 }
