@@ -1,7 +1,7 @@
 """CPU oracle: restatement of the reference's two attention processors.
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PINNED against the reference
-itself: tests/test_oracle_vs_reference.py imports /root/reference/attention.py
+itself: tests/test_oracle_cpu.py imports /root/reference/attention.py
 verbatim (via oracle/diffusers_shim) and tests/golden/ holds outputs generated
 from it by tests/golden/make_golden.py.
 

@@ -72,3 +72,41 @@ def test_oracle_matches_verbatim_reference_full_unet():
         unet.set_attn_processor(theirs)
         y_ref = unet(x, torch.tensor(500), ehs).sample
     assert torch.allclose(y_mine, y_ref, rtol=1e-4, atol=1e-5)
+
+
+# ---- independent cross-check of the (otherwise unpinned) diffusers restatement: TVM's relax port of diffusers' get_timestep_embedding
+TVM_OP = "/opt/prime-rl/.venv/lib/python3.12/site-packages/tilelang/3rdparty/tvm/python/tvm/relax/frontend/nn/op.py"
+
+
+def _run_tvm_port_with_numpy(timesteps, dim, **kw):
+    """Execute the SOURCE of tvm.relax.frontend.nn.op.get_timestep_embedding (a third-party port of the diffusers function)
+    with its relax ops bound to numpy: the port's own arithmetic graph, evaluated without a TVM runtime."""
+    import ast, math, types
+    import numpy as np
+    src = open(TVM_OP).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "get_timestep_embedding")
+    node.returns = None
+    for a in node.args.args:
+        a.annotation = None
+    code = compile(ast.Module(body=[node], type_ignores=[]), TVM_OP, "exec")
+    f32 = lambda x: np.asarray(x, dtype=np.float32)
+    op = types.SimpleNamespace(
+        astype=lambda x, dt: f32(x), arange=lambda start, end, dtype: np.arange(start, end, dtype=np.float32), exp=lambda x: np.exp(f32(x)),
+        expand_dims=lambda x, ax: np.expand_dims(x, ax), concat=lambda xs, axis: np.concatenate(xs, axis=axis), cos=lambda x: np.cos(f32(x)),
+        sin=lambda x: np.sin(f32(x)), nn=types.SimpleNamespace(pad=lambda x, p: np.pad(x, ((p[2], p[3]), (p[0], p[1])))))
+    ns = dict(math=math, _op=op, rx=types.SimpleNamespace(const=lambda v, dt: np.float32(v)), get_default_dtype=lambda: "float32",
+              wrap_nested=lambda e, name: e, Tensor=object)
+    exec(code, ns)
+    return ns["get_timestep_embedding"](types.SimpleNamespace(_expr=np.asarray(timesteps)), dim, **kw)
+
+
+@pytest.mark.skipif(not os.path.exists(TVM_OP), reason="TVM sources not in this image")
+@pytest.mark.parametrize("dim,flip,shift", [(320, True, 0.0), (256, True, 0.0), (320, False, 1.0)])
+def test_timestep_embedding_matches_the_tvm_port_of_diffusers(dim, flip, shift):
+    """unet_ref.get_timestep_embedding (diffusers 0.23 restated, parity otherwise unpinned) against an independent port of the same function."""
+    from oracle.unet_ref import get_timestep_embedding
+    t = torch.tensor([0, 1, 33, 500, 961, 999])
+    ours = get_timestep_embedding(t, dim, flip_sin_to_cos=flip, downscale_freq_shift=shift).numpy()
+    theirs = _run_tvm_port_with_numpy(t.numpy(), dim, flip_sin_to_cos=flip, downscale_freq_shift=shift)
+    assert ours.shape == theirs.shape
+    assert abs(ours - theirs).max() < 2e-4      # fp32 sin/cos of arguments up to ~1e3 rad: ulp-level differences of the product; a layout or formula mismatch would be O(1)
