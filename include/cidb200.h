@@ -76,7 +76,10 @@ int cid_attn_self(const void* Q, long long q_pitch, const void* K, long long k_p
 
 /* Decoupled text + id cross-attention: O = softmax(Q Kt^T) Vt + ip_scale * softmax(Q Ki^T) Vi, with
  * Kcat [B, 96, H*d] (rows [0,n_text) text, [80,80+n_ip) id, others zero) and Vtcat [B*H, d, 96].
- * Replaces attention.py:259-279. */
+ * Replaces attention.py:259-279.  n_text <= 80 (<= 96 without id tokens), n_ip <= 16.  Head dims <= 80 with at least one 128-query
+ * tile per SM and N > 128 run the persistent pipelined kernel (both softmaxes normalised before ONE P.V accumulation: the 16-bit
+ * rounding the reference applies to each branch before the mix sits on the probabilities); other shapes the per-tile kernel that
+ * rounds each branch as the reference does.  Both are covered by the processor golden vectors. */
 int cid_attn_cross(const void* Q, long long q_pitch, const void* Kcat, const void* Vtcat, void* O, long long ldo,
                    int B, int H, int N, int d, int n_text, int n_ip, float ip_scale, int dtype, void* stream);
 int cid_pack_cross_kv(const void* k_text, const void* v_text, const void* k_ip, const void* v_ip, void* k_cat,

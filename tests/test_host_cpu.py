@@ -97,3 +97,15 @@ def test_product_never_touches_the_oracle_or_a_compiler_stack():
         assert not bad.search(src), path
     entry = open(os.path.join(root, "__graft_entry__.py")).read()
     assert "def build" in entry and "def smoke" in entry and "compute_100a" in entry
+
+
+def test_gn_small_applicability_rule():
+    """ops.gn_small_ok mirrors cid_gn_small's contract (include/cidb200.h): 8-channel vectors inside groups, groups inside one source of the
+    virtual concat, at most 32768 elements per (sample, group)."""
+    from consistentid_b200 import ops
+    assert ops.gn_small_ok(1280, 0, 64, 32) and ops.gn_small_ok(1280, 1280, 64, 32)          # the SD1.5 8x8 level
+    assert ops.gn_small_ok(1280, 1280, 256, 32)                                              # 16x16: 20480 elements
+    assert not ops.gn_small_ok(1280, 640, 256, 32)                                           # 60 channels per group: vectors straddle groups
+    assert not ops.gn_small_ok(320, 0, 4096, 32)                                             # slab too large
+    assert not ops.gn_small_ok(640, 320, 64, 32) or (960 // 32) % 8 == 0                      # 30 channels per group
+    assert not ops.gn_small_ok(328, 0, 64, 32)                                               # C not divisible by the groups
